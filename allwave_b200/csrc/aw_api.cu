@@ -1,0 +1,990 @@
+// aw_api.cu -- C-ABI implementation of liballwave_cuda.so (see include/allwave_cuda.h).
+// Host plumbing only: sequence store upload, workspace sizing, kernel launches, the retry
+// ladder for pairs whose device workspace was too small, result delivery.  All arithmetic of
+// the path runs in the kernels of aw_wfa.cuh / aw_sketch.cuh; there is no CPU fallback.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "aw_common.cuh"
+#include "aw_sketch.cuh"
+#include "aw_wfa.cuh"
+
+static thread_local char g_err[512] = "";
+void aw_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return AW_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e != cudaSuccess) {
+            aw_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            cudaGetLastError();
+            return AW_ENOMEM;
+        }
+        cap = bytes;
+        return AW_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return AW_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            aw_set_error("cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            cudaGetLastError();
+            return AW_ENOMEM;
+        }
+        cap = want;
+        return AW_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct SketchSet {
+    DevBuf sk, n;
+    uint32_t count = 0, size = 0;
+};
+
+}  // namespace
+
+struct aw_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    // options
+    int ctas_per_sm = 0;       // 0 = auto
+    int threads_per_cta = 0;   // 0 = auto (32 for short pairs, 256 otherwise)
+    int64_t max_w = 1 << 20;   // cap on allocated diagonals per wavefront (first attempt)
+    int64_t hist_mb = 16;      // base-case history arena per CTA (first attempt)
+    int64_t chunk_pairs = 65536;
+    // sequence store
+    uint32_t n = 0;
+    std::vector<uint64_t> lens;
+    std::vector<AwSlot> h_slots;
+    std::vector<std::string> ids;
+    bool all_clean = true;
+    uint64_t max_len = 0;
+    DevBuf d_slots, d_ascii, d_packed, d_ids, d_id_off;
+    // sketches: stranded (k=15,s=1000) over 2n slots; canonical by (k, size) over n sequences
+    SketchSet stranded;
+    bool have_stranded = false;
+    std::map<std::pair<int, uint32_t>, SketchSet*> canonical;
+    // grow-only per-launch workspace (one launch in flight per context)
+    DevBuf ws_ring, ws_hist, ws_hist_meta, ws_runs;
+};
+
+struct aw_batch {
+    AwPen pen;
+    int orient = AW_ORIENT_MASH;
+    uint32_t flags = 0;
+    uint64_t npairs = 0;
+    std::vector<aw_pair> h_pairs;
+    DevBuf d_pairs, d_isrev, d_order, d_out, d_text, d_bytes, d_ctl;  // d_ctl: [0] text cursor, [1] bytes cursor, [2] next_pair
+    uint64_t text_cap = 0, bytes_cap = 0;
+    bool has_order = false;
+    uint64_t max_p = 0, max_t = 0;
+    // host copies
+    PinBuf h_out, h_text, h_bytes;
+    // retry pass results
+    std::vector<AwPairOut> r_out;
+    std::vector<uint32_t> r_idx;
+    std::vector<char> r_text;
+    std::vector<uint8_t> r_bytes;
+    uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool launched = false;
+};
+
+struct aw_aligner {
+    aw_ctx* ctx = nullptr;  // private context on the parent's device
+    aw_params params;
+    int memory_mode = AW_MEMORY_ULTRALOW;
+    int32_t score = 0;
+    std::vector<uint8_t> cigar;
+};
+
+// ------------------------------------------------------------------------------------------
+extern "C" int aw_abi_version(void) { return AW_ABI_VERSION; }
+extern "C" const char* aw_last_error(void) { return g_err; }
+extern "C" const char* aw_strerror(int s) {
+    switch (s) {
+        case AW_OK: return "ok";
+        case AW_EINVAL: return "invalid argument";
+        case AW_ENODEVICE: return "no usable CUDA device";
+        case AW_ECUDA: return "CUDA runtime error";
+        case AW_ENOMEM: return "out of memory";
+        case AW_EUNSUPPORTED: return "unsupported parameter";
+        case AW_EWORKSPACE: return "device workspace exhausted";
+        case AW_ECALLBACK: return "cancelled by callback";
+        case AW_EALIGN: return "alignment failed";
+        default: return "unknown status";
+    }
+}
+extern "C" int aw_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+extern "C" int aw_create(int device, aw_ctx** out) {
+    if (!out) return AW_EINVAL;
+    *out = nullptr;
+    int n = aw_device_count();
+    if (n <= 0 || device < 0 || device >= n) {
+        aw_set_error("no CUDA device %d (visible devices: %d); this library has no CPU fallback", device, n);
+        return AW_ENODEVICE;
+    }
+    AW_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    AW_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        aw_set_error("device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+        return AW_ENODEVICE;
+    }
+    aw_ctx* c = new aw_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        aw_set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+        delete c;
+        return AW_ECUDA;
+    }
+    *out = c;
+    return AW_OK;
+}
+
+static void free_sketches(aw_ctx* c) {
+    c->stranded.sk.release();
+    c->stranded.n.release();
+    c->have_stranded = false;
+    for (auto& kv : c->canonical) {
+        kv.second->sk.release();
+        kv.second->n.release();
+        delete kv.second;
+    }
+    c->canonical.clear();
+}
+
+extern "C" void aw_destroy(aw_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    free_sketches(c);
+    c->d_slots.release();
+    c->d_ascii.release();
+    c->d_packed.release();
+    c->d_ids.release();
+    c->d_id_off.release();
+    c->ws_ring.release();
+    c->ws_hist.release();
+    c->ws_hist_meta.release();
+    c->ws_runs.release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
+    if (!c || !key) return AW_EINVAL;
+    std::string k(key);
+    if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
+    else if (k == "threads_per_cta") {
+        if (value != 0 && value != 32 && value != 256) return AW_EINVAL;
+        c->threads_per_cta = (int)value;
+    } else if (k == "max_wavefront_width") c->max_w = value;
+    else if (k == "hist_mb") c->hist_mb = value;
+    else if (k == "chunk_pairs") c->chunk_pairs = value > 0 ? value : 65536;
+    else return AW_EINVAL;
+    return AW_OK;
+}
+
+extern "C" uint32_t aw_num_sequences(const aw_ctx* c) { return c ? c->n : 0; }
+
+extern "C" int aw_load_sequences(aw_ctx* c, uint32_t n, const uint8_t* const* seqs, const uint64_t* lens, const char* const* ids) {
+    if (!c || (n && (!seqs || !lens))) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    free_sketches(c);
+    c->n = n;
+    c->lens.assign(lens, lens + n);
+    c->ids.resize(n);
+    c->h_slots.assign((size_t)2 * n, AwSlot{0, 0, 0, 1});
+    c->max_len = 0;
+    // layout: every slot 16-byte aligned with 16 guard bytes / 4 guard words either side
+    uint64_t a_off = 16, p_off = 4, raw_total = 0;
+    std::vector<uint64_t> raw_off(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        if (lens[i] > 0x07ffffffull) {
+            aw_set_error("sequence %u is longer than 2^27-1 bases", i);
+            return AW_EUNSUPPORTED;
+        }
+        raw_off[i] = raw_total;
+        raw_total += lens[i];
+        c->max_len = std::max<uint64_t>(c->max_len, lens[i]);
+        for (int s = 0; s < 2; ++s) {
+            AwSlot& sl = c->h_slots[2 * i + s];
+            sl.ascii_off = a_off;
+            sl.packed_off = p_off;
+            sl.len = (uint32_t)lens[i];
+            sl.clean = 1;
+            a_off += ((lens[i] + 15) / 16) * 16 + 32;
+            p_off += (lens[i] + 15) / 16 + 8;
+        }
+        c->ids[i] = ids && ids[i] ? ids[i] : "";
+    }
+    // ids
+    std::vector<uint32_t> id_off(n + 1);
+    std::string idcat;
+    for (uint32_t i = 0; i < n; ++i) {
+        id_off[i] = (uint32_t)idcat.size();
+        idcat += c->ids[i];
+    }
+    id_off[n] = (uint32_t)idcat.size();
+    int rc;
+    if ((rc = c->d_slots.ensure(sizeof(AwSlot) * 2 * (size_t)std::max(1u, n)))) return rc;
+    if ((rc = c->d_ascii.ensure(a_off + 16))) return rc;
+    if ((rc = c->d_packed.ensure((p_off + 4) * 4))) return rc;
+    if ((rc = c->d_ids.ensure(idcat.size() + 1))) return rc;
+    if ((rc = c->d_id_off.ensure(4 * (size_t)(n + 1)))) return rc;
+    AW_CUDA_CHECK(cudaMemsetAsync(c->d_ascii.p, 0, a_off + 16, c->stream));
+    AW_CUDA_CHECK(cudaMemsetAsync(c->d_packed.p, 0, (p_off + 4) * 4, c->stream));
+    if (n == 0) {
+        AW_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        return AW_OK;
+    }
+    // stage raw sequences through pinned memory
+    PinBuf stage;
+    DevBuf d_raw, d_raw_off;
+    if ((rc = stage.ensure(raw_total + 16))) return rc;
+    for (uint32_t i = 0; i < n; ++i) memcpy(stage.as<uint8_t>() + raw_off[i], seqs[i], lens[i]);
+    if ((rc = d_raw.ensure(raw_total + 16)) || (rc = d_raw_off.ensure(8 * (size_t)n))) {
+        stage.release();
+        return rc;
+    }
+    cudaError_t e = cudaMemcpyAsync(d_raw.p, stage.p, raw_total, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_raw_off.p, raw_off.data(), 8 * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_slots.p, c->h_slots.data(), sizeof(AwSlot) * 2 * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_ids.p, idcat.data(), idcat.size(), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->d_id_off.p, id_off.data(), 4 * (size_t)(n + 1), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        const uint64_t maxwords = (c->max_len + 15) / 16;
+        dim3 grid((unsigned)std::max<uint64_t>(1, std::min<uint64_t>((maxwords + 127) / 128, 1024)), (unsigned)std::min<uint32_t>(n, 65535u));
+        awk::aw_pack_kernel<<<grid, 128, 0, c->stream>>>(d_raw.as<uint8_t>(), d_raw_off.as<uint64_t>(), c->d_slots.as<AwSlot>(), n,
+                                                         c->d_ascii.as<uint8_t>(), c->d_packed.as<uint32_t>());
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_slots.data(), c->d_slots.p, sizeof(AwSlot) * 2 * (size_t)n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    stage.release();
+    d_raw.release();
+    d_raw_off.release();
+    if (e != cudaSuccess) {
+        aw_set_error("aw_load_sequences: %s", cudaGetErrorString(e));
+        return AW_ECUDA;
+    }
+    c->all_clean = true;
+    for (auto& s : c->h_slots) c->all_clean = c->all_clean && s.clean;
+    return AW_OK;
+}
+
+// ---- sketches ------------------------------------------------------------------------------
+static uint32_t next_pow2(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static int build_sketches(aw_ctx* c, SketchSet& ss, bool canonical, int k, uint32_t size, cudaStream_t st) {
+    const uint32_t count = canonical ? c->n : 2 * c->n;
+    if (k < 1 || k > 31 || size == 0 || size > 4096) return AW_EINVAL;
+    int rc;
+    if ((rc = ss.sk.ensure(sizeof(uint64_t) * (size_t)std::max(1u, count) * size))) return rc;
+    if ((rc = ss.n.ensure(sizeof(uint32_t) * (size_t)std::max(1u, count)))) return rc;
+    ss.count = count;
+    ss.size = size;
+    if (count == 0) return AW_OK;
+    const uint32_t cap = next_pow2(size);
+    const size_t smem = sizeof(unsigned long long) * cap;
+    if (canonical)
+        awk::aw_sketch_kernel<true><<<count, awk::SK_NT, smem, st>>>(c->d_ascii.as<uint8_t>(), c->d_slots.as<AwSlot>(), 2, k, size, cap, ss.sk.as<uint64_t>(), ss.n.as<uint32_t>());
+    else
+        awk::aw_sketch_kernel<false><<<count, awk::SK_NT, smem, st>>>(c->d_ascii.as<uint8_t>(), c->d_slots.as<AwSlot>(), 1, k, size, cap, ss.sk.as<uint64_t>(), ss.n.as<uint32_t>());
+    AW_CUDA_CHECK(cudaGetLastError());
+    return AW_OK;
+}
+
+static int ensure_stranded(aw_ctx* c, cudaStream_t st, uint64_t* launches) {
+    if (c->have_stranded) return AW_OK;
+    int rc = build_sketches(c, c->stranded, false, AW_ORIENT_K, AW_SKETCH_SIZE, st);
+    if (rc) return rc;
+    c->have_stranded = true;
+    if (launches) ++*launches;
+    return AW_OK;
+}
+
+static int ensure_canonical(aw_ctx* c, int k, uint32_t size, SketchSet** out) {
+    auto key = std::make_pair(k, size);
+    auto it = c->canonical.find(key);
+    if (it != c->canonical.end()) {
+        *out = it->second;
+        return AW_OK;
+    }
+    SketchSet* ss = new SketchSet();
+    int rc = build_sketches(c, *ss, true, k, size, c->stream);
+    if (rc) {
+        delete ss;
+        return rc;
+    }
+    c->canonical[key] = ss;
+    *out = ss;
+    return AW_OK;
+}
+
+extern "C" int aw_get_sketch(aw_ctx* c, uint32_t idx, int reverse_complement, int canonical, int k, uint32_t sketch_size, uint64_t* out, uint32_t* out_n) {
+    if (!c || !out || !out_n || idx >= c->n) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    SketchSet* ss = nullptr;
+    uint32_t row;
+    int rc;
+    if (canonical) {
+        if ((rc = ensure_canonical(c, k, sketch_size, &ss))) return rc;
+        row = idx;
+    } else {
+        if (k != AW_ORIENT_K || sketch_size != AW_SKETCH_SIZE) return AW_EUNSUPPORTED;
+        if ((rc = ensure_stranded(c, c->stream, nullptr))) return rc;
+        ss = &c->stranded;
+        row = 2 * idx + (reverse_complement ? 1 : 0);
+    }
+    AW_CUDA_CHECK(cudaMemcpyAsync(out_n, ss->n.as<uint32_t>() + row, 4, cudaMemcpyDeviceToHost, c->stream));
+    AW_CUDA_CHECK(cudaMemcpyAsync(out, ss->sk.as<uint64_t>() + (size_t)row * ss->size, 8 * (size_t)ss->size, cudaMemcpyDeviceToHost, c->stream));
+    AW_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return AW_OK;
+}
+
+extern "C" int aw_mash_jaccard_counts(aw_ctx* c, int k, uint32_t sketch_size, uint32_t* inter, uint32_t* uni) {
+    if (!c || !inter || !uni) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    SketchSet* ss = nullptr;
+    int rc = ensure_canonical(c, k, sketch_size, &ss);
+    if (rc) return rc;
+    const size_t nn = (size_t)c->n * c->n;
+    if (nn == 0) return AW_OK;
+    DevBuf di, du;
+    if ((rc = di.ensure(4 * nn)) || (rc = du.ensure(4 * nn))) {
+        di.release();
+        return rc;
+    }
+    cudaError_t e = cudaMemsetAsync(di.p, 0, 4 * nn, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(du.p, 0, 4 * nn, c->stream);
+    if (e == cudaSuccess) {
+        awk::aw_jaccard_matrix_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->n, ss->sk.as<uint64_t>(), ss->n.as<uint32_t>(), ss->size, di.as<uint32_t>(), du.as<uint32_t>());
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(inter, di.p, 4 * nn, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(uni, du.p, 4 * nn, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    di.release();
+    du.release();
+    if (e != cudaSuccess) {
+        aw_set_error("aw_mash_jaccard_counts: %s", cudaGetErrorString(e));
+        return AW_ECUDA;
+    }
+    return AW_OK;
+}
+
+extern "C" int aw_orient_pairs(aw_ctx* c, const aw_pair* pairs, uint64_t npairs, uint8_t* out_is_reverse) {
+    if (!c || (npairs && (!pairs || !out_is_reverse))) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    for (uint64_t i = 0; i < npairs; ++i)
+        if (pairs[i].query_idx >= c->n || pairs[i].target_idx >= c->n) return AW_EINVAL;
+    if (npairs == 0) return AW_OK;
+    int rc = ensure_stranded(c, c->stream, nullptr);
+    if (rc) return rc;
+    DevBuf dp, dr;
+    if ((rc = dp.ensure(sizeof(aw_pair) * npairs)) || (rc = dr.ensure(npairs))) {
+        dp.release();
+        return rc;
+    }
+    cudaError_t e = cudaMemcpyAsync(dp.p, pairs, sizeof(aw_pair) * npairs, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        awk::aw_orient_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(dp.as<aw_pair>(), npairs, c->stranded.sk.as<uint64_t>(), c->stranded.n.as<uint32_t>(), c->stranded.size, dr.as<uint8_t>());
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_is_reverse, dr.p, npairs, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    dp.release();
+    dr.release();
+    if (e != cudaSuccess) {
+        aw_set_error("aw_orient_pairs: %s", cudaGetErrorString(e));
+        return AW_ECUDA;
+    }
+    return AW_OK;
+}
+
+// ---- batches -------------------------------------------------------------------------------
+// create_wfa_aligner + AlignmentMode::from_params (src/alignment.rs:263-289, src/types.rs:105-117)
+static int pen_from_params(const aw_params* p, AwPen* pen) {
+    memset(pen, 0, sizeof(*pen));
+    if (p->match_score != 0) {
+        aw_set_error("match_score != 0 is not supported (WFA2 penalty shifting is out of scope)");
+        return AW_EUNSUPPORTED;
+    }
+    const bool two = p->has_gap2_open && p->has_gap2_extend;
+    const bool edit = !two && p->gap_open == p->gap_extend && p->gap_open == p->mismatch_penalty;
+    pen->x = p->mismatch_penalty;
+    pen->o1 = edit ? p->mismatch_penalty : p->gap_open;
+    pen->e1 = edit ? p->mismatch_penalty : p->gap_extend;
+    pen->two_piece = two ? 1 : 0;
+    if (two) {
+        pen->o2 = p->gap2_open;
+        pen->e2 = p->gap2_extend;
+        if (pen->o2 < 0 || pen->e2 <= 0) return AW_EINVAL;
+    }
+    if (pen->x <= 0 || pen->o1 < 0 || pen->e1 <= 0) {
+        aw_set_error("penalties must satisfy mismatch>0, gap_open>=0, gap_extend>0");
+        return AW_EINVAL;
+    }
+    int sc = std::max(pen->x, pen->o1 + pen->e1);
+    if (two) sc = std::max(sc, pen->o2 + pen->e2);
+    pen->scope = sc + 1;
+    if (pen->scope > 512) {
+        aw_set_error("penalties too large (max_score_scope %d > 512)", pen->scope);
+        return AW_EUNSUPPORTED;
+    }
+    return AW_OK;
+}
+
+extern "C" void aw_batch_destroy(aw_ctx* c, aw_batch* b) {
+    if (!b) return;
+    if (c) cudaSetDevice(c->device);
+    b->d_pairs.release();
+    b->d_isrev.release();
+    b->d_order.release();
+    b->d_out.release();
+    b->d_text.release();
+    b->d_bytes.release();
+    b->d_ctl.release();
+    b->h_out.release();
+    b->h_text.release();
+    b->h_bytes.release();
+    delete b;
+}
+
+extern "C" int aw_batch_create(aw_ctx* c, const aw_params* params, int orientation_mode, const aw_pair* pairs, uint64_t npairs, uint32_t flags,
+                               aw_batch** out) {
+    if (!c || !params || !out || (npairs && !pairs)) return AW_EINVAL;
+    *out = nullptr;
+    if (npairs > 0xfffffff0ull) return AW_EINVAL;
+    if (orientation_mode == AW_ORIENT_WFA) {
+        aw_set_error("AW_ORIENT_WFA (--wfa-orientation) is not implemented yet");
+        return AW_EUNSUPPORTED;
+    }
+    if (orientation_mode != AW_ORIENT_MASH && orientation_mode != AW_ORIENT_FORWARD) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    aw_batch* b = new aw_batch();
+    int rc = pen_from_params(params, &b->pen);
+    if (rc) {
+        delete b;
+        return rc;
+    }
+    b->orient = orientation_mode;
+    b->flags = flags;
+    b->npairs = npairs;
+    b->h_pairs.assign(pairs, pairs + npairs);
+    uint64_t sum_len = 0;
+    bool varied = false;
+    for (uint64_t i = 0; i < npairs; ++i) {
+        if (pairs[i].query_idx >= c->n || pairs[i].target_idx >= c->n) {
+            aw_set_error("pair %llu references a sequence index out of range", (unsigned long long)i);
+            delete b;
+            return AW_EINVAL;
+        }
+        const uint64_t pl = c->lens[pairs[i].query_idx], tl = c->lens[pairs[i].target_idx];
+        b->max_p = std::max(b->max_p, pl);
+        b->max_t = std::max(b->max_t, tl);
+        sum_len += pl + tl;
+        if (i && (pl + tl) != c->lens[pairs[0].query_idx] + c->lens[pairs[0].target_idx]) varied = true;
+    }
+    size_t idlen_max = 0;
+    for (auto& s : c->ids) idlen_max = std::max(idlen_max, s.size());
+    b->text_cap = (flags & AW_FLAG_NO_PAF) ? sum_len / 2 + 64 * npairs + 1024 : sum_len + (256 + 2 * idlen_max) * npairs + 1024;
+    b->bytes_cap = (flags & AW_FLAG_CIGAR_BYTES) ? sum_len + 16 : 16;
+    const size_t np1 = (size_t)std::max<uint64_t>(1, npairs);
+    if ((rc = b->d_pairs.ensure(sizeof(aw_pair) * np1)) || (rc = b->d_isrev.ensure(np1)) || (rc = b->d_out.ensure(sizeof(AwPairOut) * np1)) ||
+        (rc = b->d_text.ensure(b->text_cap)) || (rc = b->d_bytes.ensure(b->bytes_cap)) || (rc = b->d_ctl.ensure(64))) {
+        aw_batch_destroy(c, b);
+        return rc;
+    }
+    cudaError_t e = cudaMemcpyAsync(b->d_pairs.p, pairs, sizeof(aw_pair) * npairs, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_isrev.p, 0, np1, c->stream);
+    if (e == cudaSuccess && varied) {
+        // heaviest (longest) pairs first: greedy balance of the persistent CTAs
+        std::vector<uint32_t> order(npairs);
+        for (uint64_t i = 0; i < npairs; ++i) order[i] = (uint32_t)i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t bb) {
+            const uint64_t la = c->lens[pairs[a].query_idx] + c->lens[pairs[a].target_idx];
+            const uint64_t lb = c->lens[pairs[bb].query_idx] + c->lens[pairs[bb].target_idx];
+            return la > lb;
+        });
+        if ((rc = b->d_order.ensure(4 * np1))) {
+            aw_batch_destroy(c, b);
+            return rc;
+        }
+        e = cudaMemcpy(b->d_order.p, order.data(), 4 * (size_t)npairs, cudaMemcpyHostToDevice);
+        b->has_order = true;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        aw_set_error("aw_batch_create: %s", cudaGetErrorString(e));
+        aw_batch_destroy(c, b);
+        return AW_ECUDA;
+    }
+    *out = b;
+    return AW_OK;
+}
+
+namespace {
+
+struct LaunchCfg {
+    int nt, grid;
+    int W;
+    unsigned long long ring_ints, hist_ints, runs_cap;
+    int hist_max_scores;
+};
+
+template <int NT, int BITS, bool TWO>
+cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStream_t st) {
+    auto kern = awk::aw_align_kernel<NT, BITS, TWO>;
+    if (smem > 40 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, NT, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, int grid, cudaStream_t st) {
+    const int scope = P.pen.scope;
+    const size_t smem = sizeof(awk::SlotMeta) * 2 * scope + sizeof(int) * ((scope * 5 + 1) & ~1) + sizeof(unsigned long long) * nt;
+#define AW_CASE(NT_, BITS_, TWO_) \
+    if (nt == NT_ && bits == BITS_ && two == TWO_) return launch_align<NT_, BITS_, TWO_>(P, grid, smem, st);
+    AW_CASE(32, 2, true)
+    AW_CASE(32, 2, false)
+    AW_CASE(32, 8, true)
+    AW_CASE(32, 8, false)
+    AW_CASE(256, 2, true)
+    AW_CASE(256, 2, false)
+    AW_CASE(256, 8, true)
+    AW_CASE(256, 8, false)
+#undef AW_CASE
+    return cudaErrorInvalidValue;
+}
+
+// sizes the per-CTA workspace for one launch; attempt 0 is the fast first try, later attempts
+// remove the wavefront-width cap and grow the history arena (retry ladder)
+int plan_launch(aw_ctx* c, const aw_batch* b, uint64_t npairs, uint64_t max_p, uint64_t max_t, int attempt, LaunchCfg* cfg) {
+    const int ncomp = b->pen.two_piece ? 5 : 3;
+    const uint64_t maxlen = std::max(max_p, max_t);
+    int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : 256);
+    int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : 2);
+    uint64_t full_w = max_p + max_t + 3;
+    uint64_t W = full_w;
+    if (attempt == 0 && W > (uint64_t)c->max_w) W = (uint64_t)c->max_w;
+    uint64_t hist_ints = (uint64_t)c->hist_mb * (1u << 20) / 4;
+    if (nt == 32 && attempt == 0) hist_ints = std::min<uint64_t>(hist_ints, 1u << 18);
+    for (int a = 0; a < attempt; ++a) hist_ints *= 8;
+    hist_ints = std::min<uint64_t>(hist_ints, 0x7fff0000ull);
+    int hist_max_scores = attempt == 0 ? (nt == 32 ? 1024 : 4096) : (attempt == 1 ? 32768 : 262144);
+    uint64_t runs_cap = max_p + max_t + 4;
+    uint64_t ring_ints = 2ull * b->pen.scope * ncomp * W;
+    uint64_t per_cta = ring_ints * 4 + hist_ints * 4 + (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 + runs_cap * 8;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return AW_ECUDA;
+    uint64_t budget = (uint64_t)((double)(free_b + c->ws_ring.cap + c->ws_hist.cap + c->ws_hist_meta.cap + c->ws_runs.cap) * 0.85);
+    uint64_t grid = (uint64_t)c->sm_count * per_sm;
+    grid = std::min<uint64_t>(grid, std::max<uint64_t>(1, npairs));
+    while (grid > 1 && grid * per_cta > budget) grid = grid / 2;
+    if (grid * per_cta > budget) {
+        aw_set_error("device workspace for one pair (%llu MB) does not fit in free memory", (unsigned long long)(per_cta >> 20));
+        return AW_ENOMEM;
+    }
+    cfg->nt = nt;
+    cfg->grid = (int)grid;
+    cfg->W = (int)std::min<uint64_t>(W, 0x7ffffff0ull);
+    cfg->ring_ints = ring_ints;
+    cfg->hist_ints = hist_ints;
+    cfg->runs_cap = runs_cap;
+    cfg->hist_max_scores = hist_max_scores;
+    int rc;
+    if ((rc = c->ws_ring.ensure(grid * ring_ints * 4)) || (rc = c->ws_hist.ensure(grid * hist_ints * 4)) ||
+        (rc = c->ws_hist_meta.ensure(grid * (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4)) || (rc = c->ws_runs.ensure(grid * runs_cap * 8)))
+        return rc;
+    return AW_OK;
+}
+
+void fill_params(aw_ctx* c, aw_batch* b, const LaunchCfg& cfg, awk::KParams* P) {
+    memset(P, 0, sizeof(*P));
+    P->slots = c->d_slots.as<AwSlot>();
+    P->packed = c->d_packed.as<uint32_t>();
+    P->ascii = c->d_ascii.as<uint8_t>();
+    P->ids = c->d_ids.as<char>();
+    P->id_off = c->d_id_off.as<uint32_t>();
+    P->pairs = b->d_pairs.as<aw_pair>();
+    P->is_reverse = b->d_isrev.as<uint8_t>();
+    P->pen = b->pen;
+    P->flags = b->flags;
+    P->ws_ring = c->ws_ring.as<int>();
+    P->ring_ints_per_cta = cfg.ring_ints;
+    P->W = cfg.W;
+    P->ws_hist = c->ws_hist.as<int>();
+    P->hist_ints_per_cta = cfg.hist_ints;
+    P->ws_hist_meta = c->ws_hist_meta.as<int>();
+    P->hist_max_scores = cfg.hist_max_scores;
+    P->ws_runs = c->ws_runs.as<uint32_t>();
+    P->runs_cap = cfg.runs_cap;
+}
+
+}  // namespace
+
+extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
+    if (!c || !b) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    memset(b->stats, 0, sizeof(b->stats));
+    b->r_out.clear();
+    b->r_idx.clear();
+    b->r_text.clear();
+    b->r_bytes.clear();
+    b->launched = true;
+    if (b->npairs == 0) return AW_OK;
+    int rc;
+    if (b->orient == AW_ORIENT_MASH) {
+        if ((rc = ensure_stranded(c, st, &b->stats[0]))) return rc;
+        awk::aw_orient_kernel<<<c->sm_count * 8, 256, 0, st>>>(b->d_pairs.as<aw_pair>(), b->npairs, c->stranded.sk.as<uint64_t>(), c->stranded.n.as<uint32_t>(),
+                                                               c->stranded.size, b->d_isrev.as<uint8_t>());
+        AW_CUDA_CHECK(cudaGetLastError());
+        ++b->stats[0];
+    }
+    LaunchCfg cfg;
+    if ((rc = plan_launch(c, b, b->npairs, b->max_p, b->max_t, 0, &cfg))) return rc;
+    AW_CUDA_CHECK(cudaMemsetAsync(b->d_ctl.p, 0, 64, st));
+    awk::KParams P;
+    fill_params(c, b, cfg, &P);
+    P.order = b->has_order ? b->d_order.as<uint32_t>() : nullptr;
+    P.npairs = (uint32_t)b->npairs;
+    P.next_pair = reinterpret_cast<unsigned int*>(b->d_ctl.as<unsigned long long>() + 2);
+    P.out = b->d_out.as<AwPairOut>();
+    P.text = b->d_text.as<char>();
+    P.text_cursor = b->d_ctl.as<unsigned long long>();
+    P.text_cap = b->text_cap;
+    P.bytes = b->d_bytes.as<uint8_t>();
+    P.bytes_cursor = b->d_ctl.as<unsigned long long>() + 1;
+    P.bytes_cap = b->bytes_cap;
+    cudaError_t e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.grid, st);
+    if (e != cudaSuccess) {
+        aw_set_error("align kernel launch (nt=%d grid=%d): %s", cfg.nt, cfg.grid, cudaGetErrorString(e));
+        return AW_ECUDA;
+    }
+    ++b->stats[0];
+    return AW_OK;
+}
+
+// re-runs the pairs that reported AW_EWORKSPACE with a larger workspace (synchronous, rare)
+static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
+    std::vector<uint32_t> failed;
+    for (uint64_t i = 0; i < b->npairs; ++i)
+        if (h_out[i].status == AW_EWORKSPACE) failed.push_back((uint32_t)i);
+    if (failed.empty()) return AW_OK;
+    b->stats[1] = failed.size();
+    for (int attempt = 1; attempt <= 3 && !failed.empty(); ++attempt) {
+        uint64_t max_p = 0, max_t = 0, sum_len = 0;
+        size_t idlen_max = 0;
+        for (uint32_t i : failed) {
+            const uint64_t pl = c->lens[b->h_pairs[i].query_idx], tl = c->lens[b->h_pairs[i].target_idx];
+            max_p = std::max(max_p, pl);
+            max_t = std::max(max_t, tl);
+            sum_len += pl + tl;
+            idlen_max = std::max(idlen_max, c->ids[b->h_pairs[i].query_idx].size() + c->ids[b->h_pairs[i].target_idx].size());
+        }
+        LaunchCfg cfg;
+        int rc = plan_launch(c, b, failed.size(), max_p, max_t, attempt, &cfg);
+        if (rc) return rc;
+        const uint64_t text_cap = 12 * sum_len + (256 + idlen_max) * failed.size() + 1024;
+        const uint64_t bytes_cap = (b->flags & AW_FLAG_CIGAR_BYTES) ? sum_len + 16 : 16;
+        DevBuf d_order, d_out, d_text, d_bytes, d_ctl;
+        if ((rc = d_order.ensure(4 * failed.size())) || (rc = d_out.ensure(sizeof(AwPairOut) * b->npairs)) || (rc = d_text.ensure(text_cap)) ||
+            (rc = d_bytes.ensure(bytes_cap)) || (rc = d_ctl.ensure(64)))
+            return rc;
+        cudaError_t e = cudaMemcpy(d_order.p, failed.data(), 4 * failed.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(d_ctl.p, 0, 64);
+        awk::KParams P;
+        fill_params(c, b, cfg, &P);
+        P.order = d_order.as<uint32_t>();
+        P.npairs = (uint32_t)failed.size();
+        P.next_pair = reinterpret_cast<unsigned int*>(d_ctl.as<unsigned long long>() + 2);
+        P.out = d_out.as<AwPairOut>();
+        P.text = d_text.as<char>();
+        P.text_cursor = d_ctl.as<unsigned long long>();
+        P.text_cap = text_cap;
+        P.bytes = d_bytes.as<uint8_t>();
+        P.bytes_cursor = d_ctl.as<unsigned long long>() + 1;
+        P.bytes_cap = bytes_cap;
+        if (e == cudaSuccess) e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.grid, c->stream);
+        ++b->stats[0];
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        std::vector<AwPairOut> outs(b->npairs);
+        unsigned long long ctl[3] = {0, 0, 0};
+        if (e == cudaSuccess) e = cudaMemcpy(outs.data(), d_out.p, sizeof(AwPairOut) * b->npairs, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(ctl, d_ctl.p, 24, cudaMemcpyDeviceToHost);
+        std::vector<char> text(std::min<uint64_t>(ctl[0], text_cap));
+        std::vector<uint8_t> bytes(std::min<uint64_t>(ctl[1], bytes_cap));
+        if (e == cudaSuccess && !text.empty()) e = cudaMemcpy(text.data(), d_text.p, text.size(), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && !bytes.empty()) e = cudaMemcpy(bytes.data(), d_bytes.p, bytes.size(), cudaMemcpyDeviceToHost);
+        d_order.release();
+        d_out.release();
+        d_text.release();
+        d_bytes.release();
+        d_ctl.release();
+        if (e != cudaSuccess) {
+            aw_set_error("retry launch: %s", cudaGetErrorString(e));
+            return AW_ECUDA;
+        }
+        std::vector<uint32_t> still;
+        for (uint32_t i : failed) {
+            AwPairOut o = outs[i];
+            if (o.status == AW_EWORKSPACE && attempt < 3) {
+                still.push_back(i);
+                continue;
+            }
+            if (o.status == AW_OK) {
+                const uint64_t toff = b->r_text.size(), boff = b->r_bytes.size();
+                b->r_text.insert(b->r_text.end(), text.begin() + o.paf_off, text.begin() + o.paf_off + o.paf_len);
+                const uint64_t nb = (b->flags & AW_FLAG_CIGAR_BYTES) ? o.n_m + o.n_x + o.n_i + o.n_d : 0;
+                if (nb) b->r_bytes.insert(b->r_bytes.end(), bytes.begin() + o.bytes_off, bytes.begin() + o.bytes_off + nb);
+                o.paf_off = toff;
+                o.bytes_off = boff;
+            }
+            b->r_idx.push_back(i);
+            b->r_out.push_back(o);
+        }
+        failed.swap(still);
+    }
+    return AW_OK;
+}
+
+extern "C" int aw_batch_fetch(aw_ctx* c, aw_batch* b, aw_result_cb cb, void* user) {
+    if (!c || !b || !b->launched) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    if (b->npairs == 0) return AW_OK;
+    // the launch may sit on a caller stream: a device-wide sync is the only portable join
+    AW_CUDA_CHECK(cudaDeviceSynchronize());
+    int rc;
+    unsigned long long ctl[3] = {0, 0, 0};
+    AW_CUDA_CHECK(cudaMemcpy(ctl, b->d_ctl.p, 24, cudaMemcpyDeviceToHost));
+    const uint64_t text_used = std::min<uint64_t>(ctl[0], b->text_cap), bytes_used = std::min<uint64_t>(ctl[1], b->bytes_cap);
+    if ((rc = b->h_out.ensure(sizeof(AwPairOut) * b->npairs)) || (rc = b->h_text.ensure(text_used + 1)) || (rc = b->h_bytes.ensure(bytes_used + 1))) return rc;
+    AW_CUDA_CHECK(cudaMemcpyAsync(b->h_out.p, b->d_out.p, sizeof(AwPairOut) * b->npairs, cudaMemcpyDeviceToHost, c->stream));
+    if (text_used) AW_CUDA_CHECK(cudaMemcpyAsync(b->h_text.p, b->d_text.p, text_used, cudaMemcpyDeviceToHost, c->stream));
+    if (bytes_used && (b->flags & AW_FLAG_CIGAR_BYTES)) AW_CUDA_CHECK(cudaMemcpyAsync(b->h_bytes.p, b->d_bytes.p, bytes_used, cudaMemcpyDeviceToHost, c->stream));
+    AW_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const AwPairOut* outs = b->h_out.as<AwPairOut>();
+    if ((rc = retry_failed(c, b, outs))) return rc;
+    std::vector<int64_t> retry_of(b->r_idx.empty() ? 0 : b->npairs, -1);
+    for (size_t j = 0; j < b->r_idx.size(); ++j) retry_of[b->r_idx[j]] = (int64_t)j;
+    b->stats[2] = text_used + b->r_text.size();
+    std::string sentinel;
+    for (uint64_t i = 0; i < b->npairs; ++i) {
+        const AwPairOut* o = &outs[i];
+        const char* text = b->h_text.as<char>();
+        const uint8_t* bytes = b->h_bytes.as<uint8_t>();
+        if (!retry_of.empty() && retry_of[i] >= 0) {
+            o = &b->r_out[retry_of[i]];
+            text = b->r_text.data();
+            bytes = b->r_bytes.data();
+        }
+        aw_result r;
+        memset(&r, 0, sizeof(r));
+        r.query_idx = b->h_pairs[i].query_idx;
+        r.target_idx = b->h_pairs[i].target_idx;
+        r.is_reverse = (uint8_t)o->is_reverse;
+        if (o->status == AW_OK) {
+            r.status = AW_OK;
+            r.score = o->score;
+            r.query_end = o->n_m + o->n_x + o->n_d;
+            r.target_end = o->n_m + o->n_x + o->n_i;
+            r.num_matches = o->n_m;
+            r.alignment_length = o->n_m + o->n_x;
+            r.paf = (b->flags & AW_FLAG_NO_PAF) ? nullptr : text + o->paf_off;
+            r.paf_len = (b->flags & AW_FLAG_NO_PAF) ? 0 : o->paf_len;
+            r.cg = text + o->paf_off + o->cg_off;
+            r.cg_len = o->paf_len - o->cg_off;
+            if (b->flags & AW_FLAG_CIGAR_BYTES) {
+                r.cigar_bytes = bytes + o->bytes_off;
+                r.cigar_len = o->n_m + o->n_x + o->n_i + o->n_d;
+            }
+            b->stats[3] += o->nruns;
+            b->stats[4] += std::max(r.query_end, r.target_end);
+            b->stats[6] += o->cells;
+            b->stats[7] += o->steps;
+        } else {
+            // the reference's failure sentinel (src/alignment.rs:49-64) still becomes a PAF line
+            r.status = AW_EALIGN;
+            r.score = INT32_MAX;
+            ++b->stats[5];
+            if (!(b->flags & AW_FLAG_NO_PAF)) {
+                char buf[128];
+                sentinel = c->ids[r.query_idx];
+                snprintf(buf, sizeof(buf), "\t%llu\t0\t0\t%c\t", (unsigned long long)c->lens[r.query_idx], r.is_reverse ? '-' : '+');
+                sentinel += buf;
+                sentinel += c->ids[r.target_idx];
+                snprintf(buf, sizeof(buf), "\t%llu\t0\t0\t0\t0\t60\tgi:f:0.000000\tcg:Z:", (unsigned long long)c->lens[r.target_idx]);
+                sentinel += buf;
+                r.paf = sentinel.data();
+                r.paf_len = sentinel.size();
+                r.cg = r.paf + r.paf_len;
+            }
+        }
+        if (cb && cb(&r, user) != 0) return AW_ECALLBACK;
+    }
+    return AW_OK;
+}
+
+extern "C" int aw_batch_stats(aw_ctx* c, aw_batch* b, uint64_t out[8]) {
+    if (!c || !b || !out) return AW_EINVAL;
+    memcpy(out, b->stats, sizeof(b->stats));
+    return AW_OK;
+}
+
+extern "C" int aw_align_pairs(aw_ctx* c, const aw_params* params, int orientation_mode, const aw_pair* pairs, uint64_t npairs, uint32_t flags,
+                              aw_result_cb cb, void* user) {
+    if (!c || !params || (npairs && !pairs)) return AW_EINVAL;
+    const uint64_t chunk = (uint64_t)c->chunk_pairs;
+    for (uint64_t off = 0; off < npairs || (npairs == 0 && off == 0); off += chunk) {
+        const uint64_t cnt = std::min<uint64_t>(chunk, npairs - off);
+        aw_batch* b = nullptr;
+        int rc = aw_batch_create(c, params, orientation_mode, pairs + off, cnt, flags, &b);
+        if (rc) return rc;
+        rc = aw_batch_launch(c, b, nullptr);
+        if (rc == AW_OK) rc = aw_batch_fetch(c, b, cb, user);
+        aw_batch_destroy(c, b);
+        if (rc) return rc;
+        if (npairs == 0) break;
+    }
+    return AW_OK;
+}
+
+// ---- lib_wfa2::AffineWavefronts-shaped API -------------------------------------------------
+static int aligner_new(aw_ctx* parent, const aw_params& p, int memory_mode, aw_aligner** out) {
+    if (!parent || !out) return AW_EINVAL;
+    *out = nullptr;
+    AwPen pen;
+    int rc = pen_from_params(&p, &pen);
+    if (rc) return rc;
+    aw_aligner* a = new aw_aligner();
+    rc = aw_create(parent->device, &a->ctx);
+    if (rc) {
+        delete a;
+        return rc;
+    }
+    a->params = p;
+    a->memory_mode = memory_mode;
+    *out = a;
+    return AW_OK;
+}
+extern "C" int aw_aligner_new_affine(aw_ctx* ctx, int32_t match_, int32_t mismatch, int32_t gap_opening, int32_t gap_extension, int memory_mode,
+                                     aw_aligner** out) {
+    aw_params p;
+    memset(&p, 0, sizeof(p));
+    p.match_score = match_;
+    p.mismatch_penalty = mismatch;
+    p.gap_open = gap_opening;
+    p.gap_extend = gap_extension;
+    // with_penalties_and_memory_mode always builds a gap-affine aligner: keep o,e distinct from the
+    // "edit" shortcut only in name -- the constructor is numerically identical
+    return aligner_new(ctx, p, memory_mode, out);
+}
+extern "C" int aw_aligner_new_affine2p(aw_ctx* ctx, int32_t match_, int32_t mismatch, int32_t gap_opening1, int32_t gap_extension1,
+                                       int32_t gap_opening2, int32_t gap_extension2, int memory_mode, aw_aligner** out) {
+    aw_params p;
+    memset(&p, 0, sizeof(p));
+    p.match_score = match_;
+    p.mismatch_penalty = mismatch;
+    p.gap_open = gap_opening1;
+    p.gap_extend = gap_extension1;
+    p.gap2_open = gap_opening2;
+    p.gap2_extend = gap_extension2;
+    p.has_gap2_open = p.has_gap2_extend = 1;
+    return aligner_new(ctx, p, memory_mode, out);
+}
+extern "C" int aw_aligner_set_alignment_scope(aw_aligner* a, int scope) { return !a ? AW_EINVAL : (scope == AW_SCOPE_ALIGNMENT ? AW_OK : AW_EUNSUPPORTED); }
+extern "C" int aw_aligner_set_alignment_span(aw_aligner* a, int span) { return !a ? AW_EINVAL : (span == AW_SPAN_END2END ? AW_OK : AW_EUNSUPPORTED); }
+extern "C" int aw_aligner_set_heuristic(aw_aligner* a, int h) { return !a ? AW_EINVAL : (h == AW_HEURISTIC_NONE ? AW_OK : AW_EUNSUPPORTED); }
+extern "C" int aw_aligner_get_memory_mode(const aw_aligner* a) { return a ? a->memory_mode : AW_EINVAL; }
+
+static int aligner_cb(const aw_result* r, void* user) {
+    aw_aligner* a = (aw_aligner*)user;
+    a->score = r->score;
+    a->cigar.assign(r->cigar_bytes, r->cigar_bytes + r->cigar_len);
+    return r->status == AW_OK ? 0 : 1;
+}
+extern "C" int aw_aligner_align(aw_aligner* a, const uint8_t* pattern, int32_t plen, const uint8_t* text, int32_t tlen) {
+    if (!a || plen < 0 || tlen < 0 || (plen && !pattern) || (tlen && !text)) return AW_ALIGN_UNDEFINED;
+    const uint8_t* seqs[2] = {pattern, text};
+    const uint64_t lens[2] = {(uint64_t)plen, (uint64_t)tlen};
+    const char* ids[2] = {"pattern", "text"};
+    a->cigar.clear();
+    a->score = INT32_MAX;
+    if (aw_load_sequences(a->ctx, 2, seqs, lens, ids) != AW_OK) return AW_ALIGN_OOM;
+    aw_pair pr = {0, 1};
+    int rc = aw_align_pairs(a->ctx, &a->params, AW_ORIENT_FORWARD, &pr, 1, AW_FLAG_CIGAR_BYTES | AW_FLAG_NO_PAF, aligner_cb, a);
+    if (rc == AW_OK) return AW_ALIGN_COMPLETED;
+    return rc == AW_ENOMEM ? AW_ALIGN_OOM : AW_ALIGN_UNDEFINED;
+}
+extern "C" int32_t aw_aligner_score(const aw_aligner* a) { return a ? a->score : INT32_MAX; }
+extern "C" const uint8_t* aw_aligner_cigar(const aw_aligner* a, uint64_t* len) {
+    if (!a) return nullptr;
+    if (len) *len = a->cigar.size();
+    return a->cigar.data();
+}
+extern "C" void aw_aligner_delete(aw_aligner* a) {
+    if (!a) return;
+    aw_destroy(a->ctx);
+    delete a;
+}

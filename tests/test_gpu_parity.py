@@ -1,0 +1,142 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, must equal the CPU oracle
+bit for bit (score, WFA2 op string, PAF line) on the same seeded inputs."""
+import random
+
+import pytest
+
+import allwave_b200 as aw
+from allwave_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+DEFAULT = dict(mismatch=5, gap_open=8, gap_extend=2, gap2_open=24, gap2_extend=1)
+EDIT = dict(mismatch=1, gap_open=1, gap_extend=1, gap2_open=None, gap2_extend=None)
+AFFINE = dict(mismatch=4, gap_open=6, gap_extend=2, gap2_open=None, gap2_extend=None)
+
+
+def _all_pairs(n):
+    return [(i, j) for i in range(n) for j in range(n) if i != j]
+
+
+def _compare(oracle, ctx, ids, seqs, pairs, pen, orientation=aw.AW_ORIENT_FORWARD, flags=aw.AW_FLAG_CIGAR_BYTES):
+    ctx.load_sequences(ids, seqs)
+    res = ctx.align_pairs(aw.make_params(**pen), pairs, orientation=orientation, flags=flags)
+    assert len(res) == len(pairs)
+    op = oracle.params(**pen)
+    bad = []
+    for r, (qi, ti) in zip(res, pairs):
+        assert (r["query_idx"], r["target_idx"]) == (qi, ti)
+        if orientation == aw.AW_ORIENT_FORWARD:
+            st, sc, ops, _ = oracle.wfa_align(op, seqs[qi], seqs[ti])
+            exp = dict(score=sc, cigar_bytes=ops, is_reverse=False)
+            exp_paf = None
+        else:
+            o = oracle.align_pair(seqs[qi], seqs[ti], qi, ti, op, use_mash=True, qname=ids[qi], tname=ids[ti])
+            exp = dict(score=o["score"], cigar_bytes=o["cigar_bytes"], is_reverse=bool(o["is_reverse"]))
+            exp_paf = o["paf"]
+        ok = r["status"] == 0 and r["score"] == exp["score"] and r["is_reverse"] == exp["is_reverse"]
+        if flags & aw.AW_FLAG_CIGAR_BYTES:
+            ok = ok and r["cigar_bytes"] == exp["cigar_bytes"]
+        ok = ok and r["cg"] == oracle.cigar_string(exp["cigar_bytes"])
+        if exp_paf is not None:
+            ok = ok and r["paf"] == exp_paf
+        if not ok:
+            bad.append((qi, ti, r["status"], r["score"], exp["score"], r["cg"][:80], oracle.cigar_string(exp["cigar_bytes"])[:80]))
+    assert not bad, f"{len(bad)}/{len(pairs)} pairs differ, first: {bad[:3]}"
+    return res
+
+
+def test_known_answers(oracle, gpu_ctx):
+    # WFA2-lib README example and the hand-derived cases of tests/debug/*.rs
+    ids = ["p", "t", "seq1", "seq2", "a12", "a10"]
+    seqs = [b"TCTTTACTCGCGCGTTGGAGAAATACAATAGT", b"TCTATACTGCGCGTTTGGAGAAATAAAATAGT", b"ACGTACGTACGT", b"ACGTACGTTCGT", b"ACGTACGTACGT", b"ACGTACGTAC"]
+    gpu_ctx.load_sequences(ids, seqs)
+    r = gpu_ctx.align_pairs(aw.make_params(**AFFINE), [(0, 1)], orientation=aw.AW_ORIENT_FORWARD, flags=aw.AW_FLAG_CIGAR_BYTES)[0]
+    assert r["score"] == -24 and r["cigar_bytes"] == b"MMMXMMMMDMMMMMMMIMMMMMMMMMXMMMMMM" and r["cg"] == "3=1X4=1I7=1D9=1X6="
+    assert r["num_matches"] == 29 and r["paf"].split("\t")[10] == "32" and "gi:f:0.935484" in r["paf"]
+    r = gpu_ctx.align_pairs(aw.make_params(**DEFAULT), [(2, 3)], orientation=aw.AW_ORIENT_FORWARD)[0]
+    assert r["paf"] == "seq1\t12\t0\t12\t+\tseq2\t12\t0\t12\t11\t12\t60\tgi:f:0.916667\tcg:Z:8=1X3="
+    r = gpu_ctx.align_pairs(aw.make_params(**DEFAULT), [(4, 5), (5, 4)], orientation=aw.AW_ORIENT_FORWARD)
+    assert r[0]["cg"] == "10=2I" and r[1]["cg"] == "10=2D"
+
+
+@pytest.mark.parametrize("pen", [DEFAULT, EDIT, AFFINE], ids=["affine2p", "edit", "affine"])
+@pytest.mark.parametrize("length,d,n", [(60, 0.05, 8), (150, 0.02, 12), (400, 0.1, 8), (1500, 0.03, 6), (3000, 0.08, 4)])
+def test_forward_parity_small(oracle, gpu_ctx, pen, length, d, n):
+    ids, seqs, _ = synth.generate(1000 + length, n, length, d)
+    _compare(oracle, gpu_ctx, ids, seqs, _all_pairs(n), pen)
+
+
+def test_edge_cases(oracle, gpu_ctx):
+    rnd = random.Random(5)
+    base = bytes(rnd.choice(b"ACGT") for _ in range(300))
+    seqs = [b"", b"A", b"ACGT", base, base, base[:150], base[150:], base[::-1], b"A" * 200, b"A" * 180 + b"C" * 20, b"ACGT" * 40, b"ACGT" * 38 + b"AC"]
+    ids = ["e%d" % i for i in range(len(seqs))]
+    for pen in (DEFAULT, EDIT):
+        _compare(oracle, gpu_ctx, ids, seqs, _all_pairs(len(seqs)), pen)
+
+
+def test_non_acgt_bytes_use_byte_path(oracle, gpu_ctx):
+    ids, seqs, _ = synth.generate(77, 4, 500, 0.04)
+    seqs[1] = seqs[1][:100] + b"NNNNnnacgt" + seqs[1][110:]
+    seqs[2] = seqs[2].lower()
+    _compare(oracle, gpu_ctx, ids, seqs, _all_pairs(4), DEFAULT)
+    _compare(oracle, gpu_ctx, ids, seqs, _all_pairs(4), DEFAULT, orientation=aw.AW_ORIENT_MASH)
+
+
+def test_c1_shape_full_paf(oracle, gpu_ctx):
+    # BASELINE config 1 shape at reduced n: 6 x 10 kb, d=1%, default scores, mash orientation
+    c, ids, seqs, _ = synth.config("C1", n=6)
+    _compare(oracle, gpu_ctx, ids, seqs, _all_pairs(6), DEFAULT, orientation=aw.AW_ORIENT_MASH)
+
+
+def test_c2_shape_sample(oracle, gpu_ctx):
+    # BASELINE config 2 shape: 10 kb at d=5% per haplotype; a few pairs (oracle ~1.6 s per pair)
+    c, ids, seqs, _ = synth.config("C2", n=4)
+    _compare(oracle, gpu_ctx, ids, seqs, [(0, 1), (1, 2), (3, 0), (2, 3)], DEFAULT, orientation=aw.AW_ORIENT_MASH)
+
+
+def test_c3_shape(oracle, gpu_ctx):
+    c, ids, seqs, _ = synth.config("C3", n=40)
+    _compare(oracle, gpu_ctx, ids, seqs, _all_pairs(40), EDIT, orientation=aw.AW_ORIENT_MASH)
+
+
+def test_c5_shape_mixed_orientation(oracle, gpu_ctx):
+    c, ids, seqs, rc = synth.config("C5", n=8)
+    assert 0 < sum(rc) < 8
+    res = _compare(oracle, gpu_ctx, ids, seqs, _all_pairs(8), DEFAULT, orientation=aw.AW_ORIENT_MASH)
+    for r in res:
+        assert r["is_reverse"] == (rc[r["query_idx"]] != rc[r["target_idx"]])
+
+
+def test_identical_sequences(gpu_ctx):
+    # reference tests/integration_tests.rs:216-260: identity 1.0, CIGAR 5000=
+    ids, seqs, _ = synth.generate(9, 1, 5000, 0.0)
+    gpu_ctx.load_sequences(["a", "b"], [seqs[0], seqs[0]])
+    r = gpu_ctx.align_pairs(aw.make_params(**DEFAULT), [(0, 1)])[0]
+    assert r["cg"] == "5000=" and r["score"] == 0 and "gi:f:1.000000" in r["paf"] and not r["is_reverse"]
+
+
+def test_sketches_and_orientation(oracle, gpu_ctx):
+    c, ids, seqs, rc = synth.config("C5", n=6, length=3000)
+    gpu_ctx.load_sequences(ids, seqs)
+    for i in range(6):
+        assert gpu_ctx.get_sketch(i) == oracle.sketch(seqs[i])
+        assert gpu_ctx.get_sketch(i, reverse_complement=True) == oracle.sketch(oracle.reverse_complement(seqs[i]))
+        assert gpu_ctx.get_sketch(i, canonical=True) == oracle.sketch(seqs[i], canonical=True)
+    pairs = _all_pairs(6)
+    assert gpu_ctx.orient_pairs(pairs) == [oracle.orientation_mash(seqs[q], seqs[t]) for q, t in pairs]
+    inter, uni = gpu_ctx.mash_jaccard_counts()
+    for i in range(6):
+        for j in range(i + 1, 6):
+            e = oracle.jaccard_counts(oracle.sketch(seqs[i], canonical=True), oracle.sketch(seqs[j], canonical=True))
+            assert (int(inter[i, j]), int(uni[i, j])) == e == (int(inter[j, i]), int(uni[j, i]))
+
+
+def test_aligner_api(oracle, gpu_ctx):
+    al = aw.Aligner(gpu_ctx, 5, 8, 2, 24, 1)
+    ids, seqs, _ = synth.generate(31, 2, 800, 0.05)
+    assert al.align(seqs[0], seqs[1]) == 0
+    st, sc, ops, _ = oracle.wfa_align(oracle.params(), seqs[0], seqs[1])
+    assert al.score() == sc and al.cigar() == ops
+    al.close()
