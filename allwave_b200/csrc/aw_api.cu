@@ -129,6 +129,7 @@ struct aw_batch {
     std::vector<uint8_t> r_bytes;
     uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool launched = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the alignment kernel of the last launch
 };
 
 struct aw_aligner {
@@ -504,6 +505,8 @@ extern "C" void aw_batch_destroy(aw_ctx* c, aw_batch* b) {
     b->h_out.release();
     b->h_text.release();
     b->h_bytes.release();
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
     delete b;
 }
 
@@ -717,11 +720,17 @@ extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
     P.bytes = b->d_bytes.as<uint8_t>();
     P.bytes_cursor = b->d_ctl.as<unsigned long long>() + 1;
     P.bytes_cap = b->bytes_cap;
+    if (!b->ev0) {
+        AW_CUDA_CHECK(cudaEventCreate(&b->ev0));
+        AW_CUDA_CHECK(cudaEventCreate(&b->ev1));
+    }
+    AW_CUDA_CHECK(cudaEventRecord(b->ev0, st));
     cudaError_t e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.grid, st);
     if (e != cudaSuccess) {
         aw_set_error("align kernel launch (nt=%d grid=%d): %s", cfg.nt, cfg.grid, cudaGetErrorString(e));
         return AW_ECUDA;
     }
+    AW_CUDA_CHECK(cudaEventRecord(b->ev1, st));
     ++b->stats[0];
     return AW_OK;
 }
@@ -883,6 +892,14 @@ extern "C" int aw_batch_fetch(aw_ctx* c, aw_batch* b, aw_result_cb cb, void* use
         }
         if (cb && cb(&r, user) != 0) return AW_ECALLBACK;
     }
+    return AW_OK;
+}
+
+extern "C" int aw_batch_kernel_ms(aw_ctx* c, aw_batch* b, float* out_ms) {
+    if (!c || !b || !out_ms || !b->ev0) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    AW_CUDA_CHECK(cudaEventSynchronize(b->ev1));
+    AW_CUDA_CHECK(cudaEventElapsedTime(out_ms, b->ev0, b->ev1));
     return AW_OK;
 }
 

@@ -131,8 +131,12 @@ int aw_batch_create(aw_ctx* ctx, const aw_params* params, int orientation_mode, 
 int aw_batch_launch(aw_ctx* ctx, aw_batch* batch, void* stream);
 int aw_batch_fetch(aw_ctx* ctx, aw_batch* batch, aw_result_cb cb, void* user);
 /* counters of the last launch: [0] kernels launched, [1] pairs retried with a larger workspace,
- * [2] PAF bytes, [3] CIGAR runs, [4] sum of block_len (PAF column 11), [5] failed pairs */
+ * [2] PAF bytes, [3] CIGAR runs, [4] sum of block_len (PAF column 11), [5] failed pairs,
+ * [6] wavefront cells computed, [7] wavefront steps ([2..7] are filled by aw_batch_fetch) */
 int aw_batch_stats(aw_ctx* ctx, aw_batch* batch, uint64_t out[8]);
+/* device time of the dominant (alignment) kernel of the last launch, from CUDA events recorded
+ * on the launch stream around that kernel alone; valid after aw_batch_fetch or a stream sync */
+int aw_batch_kernel_ms(aw_ctx* ctx, aw_batch* batch, float* out_ms);
 void aw_batch_destroy(aw_ctx* ctx, aw_batch* batch);
 
 /* ---- orientation only: out_is_reverse[i] in {0,1} for each pair (AW_ORIENT_MASH) ---- */
