@@ -160,6 +160,13 @@ def lib():
     return L
 
 
+def mode(p):
+    """AlignmentMode::from_params: 0 EditDistance, 1 SinglePieceAffine, 2 TwoPieceAffine"""
+    f = lib().awo_mode_from_params
+    f.argtypes = [C.POINTER(Params)]
+    return f(C.byref(p))
+
+
 def parse_scores(s):
     p = Params()
     rc = lib().awo_parse_scores(s.encode(), C.byref(p))
