@@ -20,7 +20,7 @@ AW_MEMORY_HIGH, AW_MEMORY_MEDIUM, AW_MEMORY_LOW, AW_MEMORY_ULTRALOW = 0, 1, 2, 3
 EXPORTS = [
     "aw_abi_version", "aw_strerror", "aw_last_error", "aw_device_count", "aw_create", "aw_destroy", "aw_set_option",
     "aw_load_sequences", "aw_num_sequences", "aw_align_pairs", "aw_batch_create", "aw_batch_launch", "aw_batch_fetch",
-    "aw_batch_stats", "aw_batch_kernel_ms", "aw_batch_destroy", "aw_orient_pairs", "aw_get_sketch", "aw_mash_jaccard_counts",
+    "aw_batch_stats", "aw_batch_kernel_ms", "aw_batch_debug_cycles", "aw_batch_destroy", "aw_orient_pairs", "aw_get_sketch", "aw_mash_jaccard_counts",
     "aw_aligner_new_affine", "aw_aligner_new_affine2p", "aw_aligner_set_alignment_scope", "aw_aligner_set_alignment_span",
     "aw_aligner_set_heuristic", "aw_aligner_get_memory_mode", "aw_aligner_align", "aw_aligner_score", "aw_aligner_cigar",
     "aw_aligner_delete",
@@ -116,6 +116,7 @@ def lib():
     L.aw_batch_fetch.argtypes = [vp, vp, RESULT_CB, vp]
     L.aw_batch_stats.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     L.aw_batch_kernel_ms.argtypes = [vp, vp, C.POINTER(C.c_float)]
+    L.aw_batch_debug_cycles.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
     L.aw_batch_destroy.argtypes = [vp, vp]
     L.aw_batch_destroy.restype = None
     L.aw_orient_pairs.argtypes = [vp, C.POINTER(AwPair), C.c_uint64, C.POINTER(C.c_uint8)]
@@ -281,6 +282,11 @@ class Batch:
         check(lib().aw_batch_stats(self.ctx._h, self._h, s), "aw_batch_stats")
         keys = ["kernels_launched", "pairs_retried", "paf_bytes", "cigar_runs", "sum_block_len", "failed_pairs", "cells", "steps"]
         return dict(zip(keys, [int(x) for x in s]))
+
+    def debug_cycles(self):
+        s = (C.c_uint64 * 6)()
+        check(lib().aw_batch_debug_cycles(self.ctx._h, self._h, s), "aw_batch_debug_cycles")
+        return dict(zip(["phase1", "phase2", "base", "backtrace", "emit", "other"], [int(x) for x in s]))
 
     def kernel_ms(self):
         ms = C.c_float()

@@ -107,7 +107,7 @@ struct aw_ctx {
     bool have_stranded = false;
     std::map<std::pair<int, uint32_t>, SketchSet*> canonical;
     // grow-only per-launch workspace (one launch in flight per context)
-    DevBuf ws_ring, ws_hist, ws_hist_meta, ws_runs;
+    DevBuf ws_main, ws_hist_meta, ws_runs;
 };
 
 struct aw_batch {
@@ -128,6 +128,7 @@ struct aw_batch {
     std::vector<char> r_text;
     std::vector<uint8_t> r_bytes;
     uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t cyc[6] = {0, 0, 0, 0, 0, 0};
     bool launched = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the alignment kernel of the last launch
 };
@@ -215,8 +216,7 @@ extern "C" void aw_destroy(aw_ctx* c) {
     c->d_packed.release();
     c->d_ids.release();
     c->d_id_off.release();
-    c->ws_ring.release();
-    c->ws_hist.release();
+    c->ws_main.release();
     c->ws_hist_meta.release();
     c->ws_runs.release();
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -228,7 +228,7 @@ extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
     std::string k(key);
     if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
     else if (k == "threads_per_cta") {
-        if (value != 0 && value != 32 && value != 256) return AW_EINVAL;
+        if (value != 0 && value != 32 && value != 128 && value != 256) return AW_EINVAL;
         c->threads_per_cta = (int)value;
     } else if (k == "max_wavefront_width") c->max_w = value;
     else if (k == "hist_mb") c->hist_mb = value;
@@ -588,7 +588,7 @@ namespace {
 struct LaunchCfg {
     int nt, grid;
     int W;
-    unsigned long long ring_ints, hist_ints, runs_cap;
+    unsigned long long ws_ints, hist_ints, runs_cap;
     int hist_max_scores;
 };
 
@@ -605,13 +605,17 @@ cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStrea
 
 cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, int grid, cudaStream_t st) {
     const int scope = P.pen.scope;
-    const size_t smem = sizeof(awk::SlotMeta) * 2 * scope + sizeof(int) * ((scope * 5 + 1) & ~1) + sizeof(unsigned long long) * nt;
+    const size_t smem = sizeof(awk::SlotMeta) * 2 * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt;
 #define AW_CASE(NT_, BITS_, TWO_) \
     if (nt == NT_ && bits == BITS_ && two == TWO_) return launch_align<NT_, BITS_, TWO_>(P, grid, smem, st);
     AW_CASE(32, 2, true)
     AW_CASE(32, 2, false)
     AW_CASE(32, 8, true)
     AW_CASE(32, 8, false)
+    AW_CASE(128, 2, true)
+    AW_CASE(128, 2, false)
+    AW_CASE(128, 8, true)
+    AW_CASE(128, 8, false)
     AW_CASE(256, 2, true)
     AW_CASE(256, 2, false)
     AW_CASE(256, 8, true)
@@ -626,21 +630,26 @@ int plan_launch(aw_ctx* c, const aw_batch* b, uint64_t npairs, uint64_t max_p, u
     const int ncomp = b->pen.two_piece ? 5 : 3;
     const uint64_t maxlen = std::max(max_p, max_t);
     int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : 256);
-    int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : 2);
+    int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : (nt == 128 ? 4 : 2));
     uint64_t full_w = max_p + max_t + 3;
     uint64_t W = full_w;
     if (attempt == 0 && W > (uint64_t)c->max_w) W = (uint64_t)c->max_w;
     uint64_t hist_ints = (uint64_t)c->hist_mb * (1u << 20) / 4;
     if (nt == 32 && attempt == 0) hist_ints = std::min<uint64_t>(hist_ints, 1u << 18);
     for (int a = 0; a < attempt; ++a) hist_ints *= 8;
-    hist_ints = std::min<uint64_t>(hist_ints, 0x7fff0000ull);
     int hist_max_scores = attempt == 0 ? (nt == 32 ? 1024 : 4096) : (attempt == 1 ? 32768 : 262144);
     uint64_t runs_cap = max_p + max_t + 4;
-    uint64_t ring_ints = 2ull * b->pen.scope * ncomp * W;
-    uint64_t per_cta = ring_ints * 4 + hist_ints * 4 + (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 + runs_cap * 8;
+    uint64_t ring_ints = 2ull * (b->pen.scope + 1) * ncomp * W;
+    if (ring_ints >= 0x7f000000ull) {
+        aw_set_error("wavefront ring of %llu ints per CTA exceeds the 32-bit workspace index", (unsigned long long)ring_ints);
+        return AW_EUNSUPPORTED;
+    }
+    hist_ints = std::min<uint64_t>(hist_ints, 0x7ff00000ull - ring_ints);
+    uint64_t ws_ints = ring_ints + hist_ints;
+    uint64_t per_cta = ws_ints * 4 + (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 + runs_cap * 8;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return AW_ECUDA;
-    uint64_t budget = (uint64_t)((double)(free_b + c->ws_ring.cap + c->ws_hist.cap + c->ws_hist_meta.cap + c->ws_runs.cap) * 0.85);
+    uint64_t budget = (uint64_t)((double)(free_b + c->ws_main.cap + c->ws_hist_meta.cap + c->ws_runs.cap) * 0.85);
     uint64_t grid = (uint64_t)c->sm_count * per_sm;
     grid = std::min<uint64_t>(grid, std::max<uint64_t>(1, npairs));
     while (grid > 1 && grid * per_cta > budget) grid = grid / 2;
@@ -651,12 +660,12 @@ int plan_launch(aw_ctx* c, const aw_batch* b, uint64_t npairs, uint64_t max_p, u
     cfg->nt = nt;
     cfg->grid = (int)grid;
     cfg->W = (int)std::min<uint64_t>(W, 0x7ffffff0ull);
-    cfg->ring_ints = ring_ints;
+    cfg->ws_ints = ws_ints;
     cfg->hist_ints = hist_ints;
     cfg->runs_cap = runs_cap;
     cfg->hist_max_scores = hist_max_scores;
     int rc;
-    if ((rc = c->ws_ring.ensure(grid * ring_ints * 4)) || (rc = c->ws_hist.ensure(grid * hist_ints * 4)) ||
+    if ((rc = c->ws_main.ensure(grid * ws_ints * 4)) ||
         (rc = c->ws_hist_meta.ensure(grid * (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4)) || (rc = c->ws_runs.ensure(grid * runs_cap * 8)))
         return rc;
     return AW_OK;
@@ -673,11 +682,10 @@ void fill_params(aw_ctx* c, aw_batch* b, const LaunchCfg& cfg, awk::KParams* P) 
     P->is_reverse = b->d_isrev.as<uint8_t>();
     P->pen = b->pen;
     P->flags = b->flags;
-    P->ws_ring = c->ws_ring.as<int>();
-    P->ring_ints_per_cta = cfg.ring_ints;
+    P->ws = c->ws_main.as<int>();
+    P->ws_ints_per_cta = cfg.ws_ints;
     P->W = cfg.W;
-    P->ws_hist = c->ws_hist.as<int>();
-    P->hist_ints_per_cta = cfg.hist_ints;
+    P->hist_ints = (int)cfg.hist_ints;
     P->ws_hist_meta = c->ws_hist_meta.as<int>();
     P->hist_max_scores = cfg.hist_max_scores;
     P->ws_runs = c->ws_runs.as<uint32_t>();
@@ -691,6 +699,7 @@ extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
     AW_CUDA_CHECK(cudaSetDevice(c->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     memset(b->stats, 0, sizeof(b->stats));
+    memset(b->cyc, 0, sizeof(b->cyc));
     b->r_out.clear();
     b->r_idx.clear();
     b->r_text.clear();
@@ -872,6 +881,7 @@ extern "C" int aw_batch_fetch(aw_ctx* c, aw_batch* b, aw_result_cb cb, void* use
             b->stats[4] += std::max(r.query_end, r.target_end);
             b->stats[6] += o->cells;
             b->stats[7] += o->steps;
+            for (int q = 0; q < 6; ++q) b->cyc[q] += o->cyc[q];
         } else {
             // the reference's failure sentinel (src/alignment.rs:49-64) still becomes a PAF line
             r.status = AW_EALIGN;
@@ -900,6 +910,12 @@ extern "C" int aw_batch_kernel_ms(aw_ctx* c, aw_batch* b, float* out_ms) {
     AW_CUDA_CHECK(cudaSetDevice(c->device));
     AW_CUDA_CHECK(cudaEventSynchronize(b->ev1));
     AW_CUDA_CHECK(cudaEventElapsedTime(out_ms, b->ev0, b->ev1));
+    return AW_OK;
+}
+
+extern "C" int aw_batch_debug_cycles(aw_ctx* c, aw_batch* b, uint64_t out[6]) {
+    if (!c || !b || !out) return AW_EINVAL;
+    memcpy(out, b->cyc, sizeof(b->cyc));
     return AW_OK;
 }
 

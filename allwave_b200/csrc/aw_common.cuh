@@ -52,6 +52,8 @@ struct AwPairOut {
     uint32_t n_breakpoints;
     uint32_t n_base;
     uint32_t max_base_score;
+    // device-clock breakdown (thread 0): phase 1, phase 2, base compute, backtrace, emission
+    unsigned long long cyc[6];
 };
 
 #define AW_CUDA_CHECK(call)                                                         \

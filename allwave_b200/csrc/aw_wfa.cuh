@@ -15,22 +15,29 @@
 
 namespace awk {
 
-constexpr int NRED = 16;       // reduction slots: [0,5) max in-bounds k, [5,10) max -k, [10,15) max antidiagonal, [15] end value
+constexpr int NRED = 16;       // reduction slots, see RED_* below
 constexpr int MAX_STACK = 96;  // DFS depth bound of the biWFA recursion
 constexpr int HIST_META_INTS = 16;
+constexpr int EDGE_ZONE = 64;  // I/D in-bounds tracking is only done this close to a wavefront end
+constexpr int SEQ_SMEM_WORDS = 4096;  // 16 KB of shared memory for the pair's packed sequences (guards included)
 
 enum { IN_MX = 0, IN_MO1, IN_I1E, IN_D1E, IN_MO2, IN_I2E, IN_D2E };
 enum { ST_OK = 0, ST_END_REACHED = 1, ST_FAIL_WORKSPACE = 2 };
+// red[] layout: per component c: RED_HI+c = max in-bounds k, RED_LO+c = max(-k); then the two
+// antidiagonal bounds and the value at the end cell
+enum { RED_HI = 0, RED_LO = 5, RED_AKM = 10, RED_AKALL = 11, RED_END = 12 };
 
 struct SlotMeta {
-    int lo[5], hi[5], ak[5];
+    int lo[5], hi[5];   // trimmed range per component; empty iff lo > hi
+    int akM;            // max antidiagonal 2*off-k over valid extended M cells (INT_MIN if none)
+    int akAll;          // upper bound of 2*off-k over every component's non-null cells
     int clo, width;     // computed (allocated) range of this wavefront (history mode)
-    unsigned off;       // history arena offset (history mode)
+    int off;            // workspace offset of the wavefront's component block (history mode)
 };
 
 struct In {
-    const int* p;  // p[k] is the offset of diagonal k
-    int lo, hi;    // trimmed range; empty iff lo > hi
+    int off;     // element k lives at ws[off + k]
+    int lo, hi;  // trimmed range; empty iff lo > hi
 };
 
 struct SubProblem {
@@ -58,12 +65,11 @@ struct KParams {
     unsigned int* next_pair;
     AwPen pen;
     uint32_t flags;
-    // per-CTA workspace
-    int* ws_ring;            // [cta][2][scope][ncomp][W]
-    unsigned long long ring_ints_per_cta;
-    int W;                   // allocated diagonals per wavefront
-    int* ws_hist;            // [cta][hist_ints]
-    unsigned long long hist_ints_per_cta;
+    // per-CTA workspace: [ring: 2 x (scope+1) x ncomp x W ints][history arena: hist_ints]
+    int* ws;
+    unsigned long long ws_ints_per_cta;
+    int W;                   // allocated diagonals per ring wavefront
+    int hist_ints;           // history arena size (ints)
     int* ws_hist_meta;       // [cta][hist_max_scores][HIST_META_INTS]
     int hist_max_scores;
     uint32_t* ws_runs;       // [cta][2][runs_cap]: pair runs, then leaf scratch
@@ -100,17 +106,17 @@ __device__ __forceinline__ void red_max(int* red, int idx, int v) {
 template <int BITS>
 __device__ __forceinline__ uint32_t load_fwd(const uint32_t* __restrict__ w, int pos) {
     constexpr int SPW = 32 / BITS;
-    const int idx = pos / SPW;  // pos >= 0
-    const int sh = (pos % SPW) * BITS;
-    return __funnelshift_r(__ldg(w + idx), __ldg(w + idx + 1), sh);
+    const unsigned idx = (unsigned)pos / SPW;  // pos >= 0
+    const int sh = ((unsigned)pos % SPW) * BITS;
+    return __funnelshift_r(w[idx], w[idx + 1], sh);
 }
 // symbols pos, pos-1, ... with `pos` in the most significant bits
 template <int BITS>
 __device__ __forceinline__ uint32_t load_rev(const uint32_t* __restrict__ w, int pos) {
     constexpr int SPW = 32 / BITS;
-    const int idx = pos / SPW;
-    const int sh = ((pos % SPW) + 1) * BITS;  // in [BITS, 32]
-    return __funnelshift_rc(__ldg(w + idx - 1), __ldg(w + idx), sh);
+    const unsigned idx = (unsigned)pos / SPW;
+    const int sh = (((unsigned)pos % SPW) + 1) * BITS;  // in [BITS, 32]
+    return __funnelshift_rc(w[(int)idx - 1], w[idx], sh);
 }
 template <int BITS>
 __device__ __forceinline__ int lcp_fwd(const uint32_t* __restrict__ pw, int pv, const uint32_t* __restrict__ tw, int th, int maxlen) {
@@ -159,87 +165,263 @@ __device__ __forceinline__ int extend_cell(const SeqView& s, int k, int off) {
     return off + n;
 }
 
-__device__ __forceinline__ int ld_in(const In& w, int k) { return (k >= w.lo && k <= w.hi) ? w.p[k] : AW_NULLV; }
+__device__ __forceinline__ int ld_in(const int* __restrict__ ws, const In& w, int k) { return (k >= w.lo && k <= w.hi) ? ws[w.off + k] : AW_NULLV; }
 
 struct StepOut {
-    int lo[5], hi[5], ak[5];
+    int lo[5], hi[5];
+    int akM, akAll;
     int endval;
+    bool ambiguous;  // an I/D trim end fell outside the tracked edge zones (needs an exact rescan)
 };
 
-// ---- K4+K5: compute wavefront s from its inputs, extend M, trim, detect termination --------
-// Restates wavefront_compute_affine2p_idm + wavefront_extend_matches_packed_end2end(_max) +
-// wavefront_compute_trim_ends + wavefront_termination_end2end.  Exactly one
-// CTA barrier; `red` must be pre-initialised to INT_MIN (triple-buffered by the caller).
+// ---- K4+K5: compute wavefront s from its inputs, extend M, and accumulate the block-wide
+// reductions (trim ends, antidiagonal bounds, end-cell value) into `red`.  No barrier here.
+// Restates wavefront_compute_affine2p_idm + wavefront_extend_matches_packed_end2end(_max)
+// (SURVEY A.2, A.3).  `red` must hold INT_MIN on entry.
 template <int NT, int BITS, bool TWO>
-__device__ __forceinline__ void wf_step(const In (&in)[7], int* const (&out)[5], int lo, int hi, const SeqView& sv, int k_end, int comp_end,
-                                        int* red, StepOut& so) {
+__device__ __forceinline__ void wf_cells(int* __restrict__ ws, const In (&in)[7], const int (&out)[5], int lo, int hi, const SeqView& sv, int k_end,
+                                         int comp_end, int* red) {
     const int tid = threadIdx.x;
     const unsigned tlen = (unsigned)sv.tlen, plen = (unsigned)sv.plen;
-    int khi[5], klo[5], akm[5];
+    // interior cells whose every input (k-1, k, k+1) is inside every input's range need no checks
+    int fast_lo = INT_MIN, fast_hi = INT_MAX;
+    {
+        bool all_present = true;
 #pragma unroll
-    for (int c = 0; c < 5; ++c) khi[c] = klo[c] = akm[c] = INT_MIN;
-    int endval = INT_MIN;
-    for (int k = lo + tid; k <= hi; k += NT) {
-        int vals[5];
-        const int i1 = max(ld_in(in[IN_MO1], k - 1), ld_in(in[IN_I1E], k - 1)) + 1;
-        const int d1 = max(ld_in(in[IN_MO1], k + 1), ld_in(in[IN_D1E], k + 1));
-        int ins = i1, del = d1;
-        vals[AW_COMP_I1] = i1;
-        vals[AW_COMP_D1] = d1;
-        if (TWO) {
-            const int i2 = max(ld_in(in[IN_MO2], k - 1), ld_in(in[IN_I2E], k - 1)) + 1;
-            const int d2 = max(ld_in(in[IN_MO2], k + 1), ld_in(in[IN_D2E], k + 1));
-            vals[AW_COMP_I2] = i2;
-            vals[AW_COMP_D2] = d2;
-            ins = max(ins, i2);
-            del = max(del, d2);
-        } else {
-            vals[AW_COMP_I2] = vals[AW_COMP_D2] = AW_NULLV;
+        for (int i = 0; i < 7; ++i) {
+            if (!TWO && i >= IN_MO2) continue;
+            all_present = all_present && (in[i].lo <= in[i].hi);
+            fast_lo = max(fast_lo, in[i].lo + 1);
+            fast_hi = min(fast_hi, in[i].hi - 1);
         }
-        const int mis = ld_in(in[IN_MX], k) + 1;
-        int m = max(del, max(mis, ins));
-        if ((unsigned)m > tlen || (unsigned)(m - k) > plen) m = AW_NULLV;
-        if (m >= 0) m = extend_cell<BITS>(sv, k, m);
-        vals[AW_COMP_M] = m;
-#pragma unroll
-        for (int c = 0; c < 5; ++c) {
-            if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
-            const int v = vals[c];
-            out[c][k] = v;
-            if ((unsigned)v <= tlen && (unsigned)(v - k) <= plen) {  // in bounds: survives the trim
-                if (klo[c] == INT_MIN) klo[c] = -k;
-                khi[c] = k;
-            }
-            if (v >= 0) akm[c] = max(akm[c], 2 * v - k);
+        if (!all_present) {
+            fast_lo = 1;
+            fast_hi = 0;
         }
-        if (k == k_end) endval = vals[comp_end];
     }
+    const bool narrow = (hi - lo) < 2 * EDGE_ZONE;
+    int m_hi = INT_MIN, m_lo = INT_MIN, akM = INT_MIN, akAll = INT_MIN, endval = INT_MIN;
+    int i1_hi = INT_MIN, i1_lo = INT_MIN, d1_hi = INT_MIN, d1_lo = INT_MIN;
+    int i2_hi = INT_MIN, i2_lo = INT_MIN, d2_hi = INT_MIN, d2_lo = INT_MIN;
+    // running pointers: one per input / output array, advanced by NT per iteration, so the loop
+    // body addresses everything with immediate offsets (no per-access 64-bit arithmetic)
+    const int k0 = lo + tid;
+    const int* p_mx = ws + in[IN_MX].off + k0;
+    const int* p_mo1 = ws + in[IN_MO1].off + k0;
+    const int* p_i1e = ws + in[IN_I1E].off + k0;
+    const int* p_d1e = ws + in[IN_D1E].off + k0;
+    const int* p_mo2 = ws + in[IN_MO2].off + k0;
+    const int* p_i2e = ws + in[IN_I2E].off + k0;
+    const int* p_d2e = ws + in[IN_D2E].off + k0;
+    int* q_m = ws + out[AW_COMP_M] + k0;
+    int* q_i1 = ws + out[AW_COMP_I1] + k0;
+    int* q_d1 = ws + out[AW_COMP_D1] + k0;
+    int* q_i2 = ws + out[AW_COMP_I2] + k0;
+    int* q_d2 = ws + out[AW_COMP_D2] + k0;
+    // one cell: recurrences, bounds, extend, stores, trim / antidiagonal tracking
+    auto cell = [&](int k, int j, int mo1l, int mo1r, int i1l, int d1r, int mo2l, int mo2r, int i2l, int d2r, int mx) {
+        const int i1 = max(mo1l, i1l) + 1;
+        const int d1 = max(mo1r, d1r);
+        int i2 = AW_NULLV, d2 = AW_NULLV, ins = i1, del = d1;
+        if (TWO) {
+            i2 = max(mo2l, i2l) + 1;
+            d2 = max(mo2r, d2r);
+            ins = max(i1, i2);
+            del = max(d1, d2);
+        }
+        int m = max(del, max(mx + 1, ins));
+        if (m >= 0) akAll = max(akAll, 2 * m - k);  // m (pre-null) dominates every component at k
+        if ((unsigned)m > tlen || (unsigned)(m - k) > plen) m = AW_NULLV;
+        if (m >= 0) {
+            m = extend_cell<BITS>(sv, k, m);
+            if (m_lo == INT_MIN) m_lo = -k;
+            m_hi = k;
+            akM = max(akM, 2 * m - k);
+        }
+        q_m[j * NT] = m;
+        q_i1[j * NT] = i1;
+        q_d1[j * NT] = d1;
+        if (TWO) {
+            q_i2[j * NT] = i2;
+            q_d2[j * NT] = d2;
+        }
+        if (narrow || k - lo < EDGE_ZONE || hi - k < EDGE_ZONE) {
+            // wavefront_compute_trim_ends keeps [first, last] in-bounds cell of every component
+            if ((unsigned)i1 <= tlen && (unsigned)(i1 - k) <= plen) {
+                if (i1_lo == INT_MIN) i1_lo = -k;
+                i1_hi = k;
+            }
+            if ((unsigned)d1 <= tlen && (unsigned)(d1 - k) <= plen) {
+                if (d1_lo == INT_MIN) d1_lo = -k;
+                d1_hi = k;
+            }
+            if (TWO) {
+                if ((unsigned)i2 <= tlen && (unsigned)(i2 - k) <= plen) {
+                    if (i2_lo == INT_MIN) i2_lo = -k;
+                    i2_hi = k;
+                }
+                if ((unsigned)d2 <= tlen && (unsigned)(d2 - k) <= plen) {
+                    if (d2_lo == INT_MIN) d2_lo = -k;
+                    d2_hi = k;
+                }
+            }
+        }
+        if (k == k_end) endval = (comp_end == AW_COMP_M) ? m : (comp_end == AW_COMP_I1) ? i1 : (comp_end == AW_COMP_D1) ? d1 : (comp_end == AW_COMP_I2) ? i2 : d2;
+    };
+    auto advance = [&](int n) {
+        p_mx += n;
+        p_mo1 += n;
+        p_i1e += n;
+        p_d1e += n;
+        q_m += n;
+        q_i1 += n;
+        q_d1 += n;
+        if (TWO) {
+            p_mo2 += n;
+            p_i2e += n;
+            p_d2e += n;
+            q_i2 += n;
+            q_d2 += n;
+        }
+    };
+    constexpr int J = 4;  // cells per thread whose global loads are issued back to back
+    int k = k0;
+    // batched interior: all J cells of this thread are unchecked, 9*J loads in flight at once
+    while (k >= fast_lo && k + (J - 1) * NT <= fast_hi && k + (J - 1) * NT <= hi) {
+        int a[J][9];
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            a[j][0] = p_mo1[j * NT - 1];
+            a[j][1] = p_mo1[j * NT + 1];
+            a[j][2] = p_i1e[j * NT - 1];
+            a[j][3] = p_d1e[j * NT + 1];
+            if (TWO) {
+                a[j][4] = p_mo2[j * NT - 1];
+                a[j][5] = p_mo2[j * NT + 1];
+                a[j][6] = p_i2e[j * NT - 1];
+                a[j][7] = p_d2e[j * NT + 1];
+            } else {
+                a[j][4] = a[j][5] = a[j][6] = a[j][7] = AW_NULLV;
+            }
+            a[j][8] = p_mx[j * NT];
+        }
+#pragma unroll
+        for (int j = 0; j < J; ++j) cell(k + j * NT, j, a[j][0], a[j][1], a[j][2], a[j][3], a[j][4], a[j][5], a[j][6], a[j][7], a[j][8]);
+        k += J * NT;
+        advance(J * NT);
+    }
+    // edges and remainders: one checked cell at a time
+    for (; k <= hi; k += NT) {
+        auto ck = [&](const In& w, const int* p, int d) -> int { return (k + d >= w.lo && k + d <= w.hi) ? p[d] : AW_NULLV; };
+        const int mo1l = ck(in[IN_MO1], p_mo1, -1), mo1r = ck(in[IN_MO1], p_mo1, 1);
+        const int i1l = ck(in[IN_I1E], p_i1e, -1), d1r = ck(in[IN_D1E], p_d1e, 1);
+        int mo2l = AW_NULLV, mo2r = AW_NULLV, i2l = AW_NULLV, d2r = AW_NULLV;
+        if (TWO) {
+            mo2l = ck(in[IN_MO2], p_mo2, -1);
+            mo2r = ck(in[IN_MO2], p_mo2, 1);
+            i2l = ck(in[IN_I2E], p_i2e, -1);
+            d2r = ck(in[IN_D2E], p_d2e, 1);
+        }
+        const int mx = ck(in[IN_MX], p_mx, 0);
+        cell(k, 0, mo1l, mo1r, i1l, d1r, mo2l, mo2r, i2l, d2r, mx);
+        advance(NT);
+    }
+    red_max<NT>(red, RED_HI + AW_COMP_M, m_hi);
+    red_max<NT>(red, RED_LO + AW_COMP_M, m_lo);
+    red_max<NT>(red, RED_AKM, akM);
+    red_max<NT>(red, RED_AKALL, akAll);
+    red_max<NT>(red, RED_HI + AW_COMP_I1, i1_hi);
+    red_max<NT>(red, RED_LO + AW_COMP_I1, i1_lo);
+    red_max<NT>(red, RED_HI + AW_COMP_D1, d1_hi);
+    red_max<NT>(red, RED_LO + AW_COMP_D1, d1_lo);
+    if (TWO) {
+        red_max<NT>(red, RED_HI + AW_COMP_I2, i2_hi);
+        red_max<NT>(red, RED_LO + AW_COMP_I2, i2_lo);
+        red_max<NT>(red, RED_HI + AW_COMP_D2, d2_hi);
+        red_max<NT>(red, RED_LO + AW_COMP_D2, d2_lo);
+    }
+    red_max<NT>(red, RED_END, endval);
+}
+
+// after the barrier: trimmed ranges (wavefront_compute_trim_ends) from the reductions
+template <bool TWO>
+__device__ __forceinline__ void wf_finish(const int* red, int lo, int hi, StepOut& so) {
+    const bool narrow = (hi - lo) < 2 * EDGE_ZONE;
+    so.ambiguous = false;
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-        if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
-        red_max<NT>(red, c, khi[c]);
-        red_max<NT>(red, 5 + c, klo[c]);
-        red_max<NT>(red, 10 + c, akm[c]);
+        if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) {
+            so.lo[c] = 1;
+            so.hi[c] = 0;
+            continue;
+        }
+        const int h = red[RED_HI + c], l = red[RED_LO + c];
+        if (h == INT_MIN) {  // nothing in bounds (among the tracked cells)
+            so.lo[c] = lo;
+            so.hi[c] = lo - 1;
+            if (c != AW_COMP_M && !narrow) so.ambiguous = true;
+        } else {
+            so.lo[c] = -l;
+            so.hi[c] = h;
+            // exact only if each end was found inside its tracked zone
+            if (c != AW_COMP_M && !narrow && ((-l) - lo >= EDGE_ZONE || hi - h >= EDGE_ZONE)) so.ambiguous = true;
+        }
     }
-    red_max<NT>(red, 15, endval);
+    so.akM = red[RED_AKM];
+    so.akAll = red[RED_AKALL];
+    so.endval = red[RED_END];
+}
+
+// exact trim of every I/D component by re-reading the stored wavefront (rare slow path)
+template <int NT, bool TWO>
+__device__ __noinline__ void wf_rescan(const int* __restrict__ ws, const int (&out)[5], int lo, int hi, int plen_, int tlen_, int* red, StepOut& so) {
+    const unsigned tlen = (unsigned)tlen_, plen = (unsigned)plen_;
+    cta_sync<NT>();
+    if (threadIdx.x < NRED) red[threadIdx.x] = INT_MIN;
+    cta_sync<NT>();
+    int vhi[5], vlo[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) vhi[c] = vlo[c] = INT_MIN;
+    for (int k = lo + (int)threadIdx.x; k <= hi; k += NT) {
+#pragma unroll
+        for (int c = 1; c < 5; ++c) {
+            if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
+            const int v = ws[out[c] + k];
+            if ((unsigned)v <= tlen && (unsigned)(v - k) <= plen) {
+                if (vlo[c] == INT_MIN) vlo[c] = -k;
+                vhi[c] = k;
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 1; c < 5; ++c) {
+        if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
+        red_max<NT>(red, RED_HI + c, vhi[c]);
+        red_max<NT>(red, RED_LO + c, vlo[c]);
+    }
     cta_sync<NT>();
 #pragma unroll
-    for (int c = 0; c < 5; ++c) {
-        const int h = red[c], l = red[5 + c];
-        if (h == INT_MIN) {  // nothing in bounds: trimmed to empty (lo kept, hi = lo-1)
+    for (int c = 1; c < 5; ++c) {
+        if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
+        const int h = red[RED_HI + c], l = red[RED_LO + c];
+        if (h == INT_MIN) {
             so.lo[c] = lo;
             so.hi[c] = lo - 1;
         } else {
             so.lo[c] = -l;
             so.hi[c] = h;
         }
-        so.ak[c] = red[10 + c];
     }
-    so.endval = red[15];
+    so.ambiguous = false;
+    cta_sync<NT>();
+    if (threadIdx.x < NRED) red[threadIdx.x] = INT_MIN;
+    cta_sync<NT>();
 }
 
 __device__ __forceinline__ bool end_reached(const StepOut& so, int comp_end, int k_end, int tlen) {
-    return so.lo[comp_end] <= k_end && k_end <= so.hi[comp_end] && so.endval >= tlen;
+    const int l = (comp_end == AW_COMP_M) ? so.lo[0] : (comp_end == AW_COMP_I1) ? so.lo[1] : (comp_end == AW_COMP_I2) ? so.lo[2] : (comp_end == AW_COMP_D1) ? so.lo[3] : so.lo[4];
+    const int h = (comp_end == AW_COMP_M) ? so.hi[0] : (comp_end == AW_COMP_I1) ? so.hi[1] : (comp_end == AW_COMP_I2) ? so.hi[2] : (comp_end == AW_COMP_D1) ? so.hi[3] : so.hi[4];
+    return l <= k_end && k_end <= h && so.endval >= tlen;
 }
 
 // number of decimal digits of v
@@ -299,32 +481,47 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
 // The kernel
 // ------------------------------------------------------------------------------------------
 template <int NT, int BITS, bool TWO>
-__global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
+__global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_align_kernel(const KParams P) {
     constexpr int NCOMP = TWO ? 5 : 3;
     extern __shared__ unsigned long long smem_raw[];
     const int scope = P.pen.scope;
-    SlotMeta* ring_meta = reinterpret_cast<SlotMeta*>(smem_raw);          // [2][scope]
-    int* hitk = reinterpret_cast<int*>(ring_meta + 2 * scope);           // [scope*5]
-    unsigned long long* scanbuf = reinterpret_cast<unsigned long long*>(hitk + ((scope * 5 + 1) & ~1));  // [NT]
-    __shared__ int red[3][NRED];
+    const int ring_n = scope + 1;  // one spare slot: the reverse step is computed speculatively
+    SlotMeta* ring_meta = reinterpret_cast<SlotMeta*>(smem_raw);                                     // [2][ring_n]
+    int* cand = reinterpret_cast<int*>(ring_meta + 2 * ring_n);                                     // [scope*5] candidate tests
+    int* hitk = cand + scope * 5;                                                                    // [scope*5] first hit per candidate
+    unsigned long long* scanbuf = reinterpret_cast<unsigned long long*>(hitk + scope * 5);  // [NT]; 8-byte aligned: 60*2*ring_n + 40*scope
+    __shared__ int red[2][3][NRED];
     __shared__ SubProblem stack[MAX_STACK];
     __shared__ unsigned s_next;
     __shared__ unsigned s_nruns;
+    __shared__ int s_ncand;
     __shared__ unsigned long long s_acc[8];
     __shared__ unsigned long long s_text_off, s_bytes_off;
+    __shared__ uint32_t s_seq[SEQ_SMEM_WORDS];
 
     const int tid = threadIdx.x;
     const AwPen pen = P.pen;
-    int* const ring_base = P.ws_ring + (size_t)blockIdx.x * P.ring_ints_per_cta;
-    int* const hist_base = P.ws_hist + (size_t)blockIdx.x * P.hist_ints_per_cta;
+    int* const ws = P.ws + (size_t)blockIdx.x * P.ws_ints_per_cta;
+    const int W = P.W;
+    const int hist_base = 2 * ring_n * NCOMP * W;  // history arena starts after the rings
     int* const hist_meta = P.ws_hist_meta + (size_t)blockIdx.x * (size_t)P.hist_max_scores * HIST_META_INTS;
     uint32_t* const pair_runs = P.ws_runs + (size_t)blockIdx.x * 2 * P.runs_cap;
     uint32_t* const leaf_runs = pair_runs + P.runs_cap;
-    const int W = P.W;
 
-    if (tid < 3 * NRED) (&red[0][0])[tid] = INT_MIN;
-    int red_i = 0;  // rotating reduction buffer (uniform)
+    if (tid < 2 * 3 * NRED) (&red[0][0][0])[tid] = INT_MIN;
+    int red_i = 0;  // rotating reduction buffer index (uniform)
     cta_sync<NT>();
+
+    auto comp_idx = [](int c) -> int { return TWO ? c : (c == AW_COMP_D1 ? 2 : c); };
+    auto rotate_red = [&]() {
+        // recycle the buffers used two steps ago (everybody finished reading them before the last barrier)
+        const int nxt = (red_i + 2) % 3;
+        if (tid < NRED) {
+            red[0][nxt][tid] = INT_MIN;
+            red[1][nxt][tid] = INT_MIN;
+        }
+        red_i = (red_i + 1) % 3;
+    };
 
     for (;;) {
         if (tid == 0) s_next = atomicAdd(P.next_pair, 1u);
@@ -337,13 +534,31 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
         const unsigned is_rev = P.is_reverse ? P.is_reverse[pair_i] : 0u;
         const AwSlot qs = P.slots[2 * pr.query_idx + is_rev];
         const AwSlot ts = P.slots[2 * pr.target_idx];
-        const uint32_t* const pw = (BITS == 2) ? P.packed + qs.packed_off : reinterpret_cast<const uint32_t*>(P.ascii + qs.ascii_off);
-        const uint32_t* const tw = (BITS == 2) ? P.packed + ts.packed_off : reinterpret_cast<const uint32_t*>(P.ascii + ts.ascii_off);
+        const uint32_t* pw = (BITS == 2) ? P.packed + qs.packed_off : reinterpret_cast<const uint32_t*>(P.ascii + qs.ascii_off);
+        const uint32_t* tw = (BITS == 2) ? P.packed + ts.packed_off : reinterpret_cast<const uint32_t*>(P.ascii + ts.ascii_off);
         const int PLEN = (int)qs.len, TLEN = (int)ts.len;
+        {
+            // stage both sequences (with 2 guard words either side) in shared memory when they fit
+            constexpr int SPW = 32 / BITS;
+            const int pwords = PLEN / SPW + 1, twords = TLEN / SPW + 1;
+            if (pwords + twords + 8 <= SEQ_SMEM_WORDS) {
+                for (int i = tid; i < pwords + 4; i += NT) s_seq[i] = pw[i - 2];
+                for (int i = tid; i < twords + 4; i += NT) s_seq[pwords + 4 + i] = tw[i - 2];
+                pw = s_seq + 2;
+                tw = s_seq + pwords + 4 + 2;
+            }
+        }
         const int koff = min(PLEN + 1, W / 2);  // diagonal k lives at index k + koff
         const int kmin_alloc = -koff, kmax_alloc = W - 1 - koff;
 
         int status = ST_OK;
+        unsigned long long cyc[6] = {0, 0, 0, 0, 0, 0};
+        long long tmark = clock64();
+        auto lap = [&](int i) {
+            const long long t = clock64();
+            cyc[i] += (unsigned long long)(t - tmark);
+            tmark = t;
+        };
         unsigned long long w_cells = 0;
         unsigned w_steps = 0, w_bps = 0, w_base = 0, w_maxbase = 0;
         if (tid == 0) s_nruns = 0;
@@ -364,6 +579,46 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
             } else if (n < P.runs_cap) {
                 pair_runs[n] = (len << 2) | op;
                 s_nruns = n + 1;
+            }
+        };
+        auto set_empty = [&](SlotMeta& m) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                m.lo[c] = 1;
+                m.hi[c] = 0;
+            }
+            m.akM = m.akAll = INT_MIN;
+            m.clo = 0;
+            m.width = 0;
+            m.off = 0;
+        };
+        auto store_meta = [&](SlotMeta& m, const StepOut& so) {
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+                m.lo[c] = so.lo[c];
+                m.hi[c] = so.hi[c];
+            }
+            m.akM = so.akM;
+            m.akAll = so.akAll;
+        };
+        // wavefront_compute_limits_input over the non-empty inputs
+        auto limits = [&](const In (&in)[7], int& lo, int& hi) {
+            lo = INT_MAX;
+            hi = INT_MIN;
+            auto lim = [&](const In& w, int dl, int dh) {
+                if (w.lo <= w.hi) {
+                    lo = min(lo, w.lo + dl);
+                    hi = max(hi, w.hi + dh);
+                }
+            };
+            lim(in[IN_MX], 0, 0);
+            lim(in[IN_MO1], -1, 1);
+            lim(in[IN_I1E], 1, 1);
+            lim(in[IN_D1E], -1, -1);
+            if (TWO) {
+                lim(in[IN_MO2], -1, 1);
+                lim(in[IN_I2E], 1, 1);
+                lim(in[IN_D2E], -1, -1);
             }
         };
 
@@ -392,200 +647,201 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
                 svd[0] = SeqView{pw, tw, sp.pb, sp.tb, plen, tlen, false};
                 svd[1] = SeqView{pw, tw, sp.pe - 1, sp.te - 1, plen, tlen, true};
                 const int cbeg[2] = {sp.cb, sp.ce}, cend[2] = {sp.ce, sp.cb};
-                auto ring_ptr = [&](int d, int slot, int c) -> int* {
-                    return ring_base + ((size_t)((d * scope + slot) * NCOMP + (TWO ? c : (c == AW_COMP_D1 ? 2 : c)))) * (size_t)W + koff;
-                };
-                auto set_empty = [&](SlotMeta& m) {
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        m.lo[c] = 1;
-                        m.hi[c] = 0;
-                        m.ak[c] = INT_MIN;
-                    }
+                int cur_slot[2] = {0, 0};  // ring slot of the newest committed/computed score per direction
+                auto ring_off = [&](int d, int slot, int c) -> int { return ((d * ring_n + slot) * NCOMP + comp_idx(c)) * W + koff; };
+                auto slot_back = [&](int slot, int back) -> int {  // slot of (score - back), back <= scope
+                    const int s = slot - back;
+                    return s < 0 ? s + ring_n : s;
                 };
                 // score-0 wavefront of direction d (wavefront_unialign_init_end2end) + extend
                 auto init_dir = [&](int d, StepOut& so) {
-                    int* r = red[red_i];
+                    int* r = red[d][red_i];
                     if (tid == 0) {
                         int m = 0;
                         if (cbeg[d] == AW_COMP_M) m = extend_cell<BITS>(svd[d], 0, 0);
-                        ring_ptr(d, 0, cbeg[d])[0] = m;
-                        r[cbeg[d]] = 0;
-                        r[5 + cbeg[d]] = 0;
-                        r[10 + cbeg[d]] = 2 * m;
-                        if (cbeg[d] == AW_COMP_M && cend[d] == AW_COMP_M && k_end == 0) r[15] = m;
+                        ws[ring_off(d, 0, cbeg[d])] = m;
+                        r[RED_AKM] = (cbeg[d] == AW_COMP_M) ? 2 * m : INT_MIN;
+                        r[RED_AKALL] = 2 * m;
+                        if (cbeg[d] == AW_COMP_M && cend[d] == AW_COMP_M && k_end == 0) r[RED_END] = m;
                     }
                     cta_sync<NT>();
-                    SlotMeta& mt = ring_meta[d * scope + 0];
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
-                        const bool on = (c == cbeg[d]);
-                        so.lo[c] = on ? 0 : 1;
-                        so.hi[c] = on ? 0 : 0;
-                        so.ak[c] = on ? r[10 + c] : INT_MIN;
-                        mt.lo[c] = so.lo[c];
-                        mt.hi[c] = on ? 0 : 0;
-                        mt.ak[c] = so.ak[c];
+                        so.lo[c] = (c == cbeg[d]) ? 0 : 1;
+                        so.hi[c] = 0;
                     }
-                    so.endval = r[15];
-                    // recycle the buffer used two steps ago
-                    const int nxt = (red_i + 2) % 3;
-                    if (tid < NRED) red[nxt][tid] = INT_MIN;
-                    red_i = (red_i + 1) % 3;
+                    so.akM = r[RED_AKM];
+                    so.akAll = r[RED_AKALL];
+                    so.endval = r[RED_END];
+                    so.ambiguous = false;
+                    cur_slot[d] = 0;
+                    store_meta(ring_meta[d * ring_n + 0], so);
+                    rotate_red();
                 };
-                // compute + extend wavefront `s` of direction d; returns true on END_REACHED
-                auto step_dir = [&](int d, int s, StepOut& so) -> bool {
+                // what survives of a step until its barrier: the computed range (null step iff lo > hi)
+                struct Range {
+                    int lo, hi;
+                };
+                auto out_offsets = [&](int d, int slot, int (&out)[5]) {
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) out[c] = ring_off(d, slot, (TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M);
+                };
+                // descriptors + limits + cell loop of wavefront `s` (ring slot `slot`) of direction d; no barrier
+                auto launch_dir = [&](int d, int s, int slot) -> Range {
                     In in[7];
-                    auto fetch = [&](int c, int score) -> In {
+                    auto fetch = [&](int c, int back) -> In {
                         In w;
-                        if (score < 0) {
-                            w.p = nullptr;
+                        if (s - back < 0) {
+                            w.off = 0;
                             w.lo = 1;
                             w.hi = 0;
                             return w;
                         }
-                        const int slot = score % scope;
-                        const SlotMeta& m = ring_meta[d * scope + slot];
-                        w.p = ring_ptr(d, slot, c);
+                        const int sl = slot_back(slot, back);
+                        const SlotMeta& m = ring_meta[d * ring_n + sl];
+                        w.off = ring_off(d, sl, c);
                         w.lo = m.lo[c];
                         w.hi = m.hi[c];
                         return w;
                     };
-                    in[IN_MX] = fetch(AW_COMP_M, s - pen.x);
-                    in[IN_MO1] = fetch(AW_COMP_M, s - pen.o1 - pen.e1);
-                    in[IN_I1E] = fetch(AW_COMP_I1, s - pen.e1);
-                    in[IN_D1E] = fetch(AW_COMP_D1, s - pen.e1);
+                    in[IN_MX] = fetch(AW_COMP_M, pen.x);
+                    in[IN_MO1] = fetch(AW_COMP_M, pen.o1 + pen.e1);
+                    in[IN_I1E] = fetch(AW_COMP_I1, pen.e1);
+                    in[IN_D1E] = fetch(AW_COMP_D1, pen.e1);
                     if (TWO) {
-                        in[IN_MO2] = fetch(AW_COMP_M, s - pen.o2 - pen.e2);
-                        in[IN_I2E] = fetch(AW_COMP_I2, s - pen.e2);
-                        in[IN_D2E] = fetch(AW_COMP_D2, s - pen.e2);
+                        in[IN_MO2] = fetch(AW_COMP_M, pen.o2 + pen.e2);
+                        in[IN_I2E] = fetch(AW_COMP_I2, pen.e2);
+                        in[IN_D2E] = fetch(AW_COMP_D2, pen.e2);
                     } else {
-                        in[IN_MO2] = in[IN_I2E] = in[IN_D2E] = fetch(AW_COMP_M, -1);
+                        in[IN_MO2].off = in[IN_I2E].off = in[IN_D2E].off = 0;
+                        in[IN_MO2].lo = in[IN_I2E].lo = in[IN_D2E].lo = 1;
+                        in[IN_MO2].hi = in[IN_I2E].hi = in[IN_D2E].hi = 0;
                     }
-                    // wavefront_compute_limits_input over the non-empty inputs
-                    int lo = INT_MAX, hi = INT_MIN;
-                    auto lim = [&](const In& w, int dl, int dh) {
-                        if (w.lo <= w.hi) {
-                            lo = min(lo, w.lo + dl);
-                            hi = max(hi, w.hi + dh);
-                        }
-                    };
-                    lim(in[IN_MX], 0, 0);
-                    lim(in[IN_MO1], -1, 1);
-                    lim(in[IN_I1E], 1, 1);
-                    lim(in[IN_D1E], -1, -1);
-                    if (TWO) {
-                        lim(in[IN_MO2], -1, 1);
-                        lim(in[IN_I2E], 1, 1);
-                        lim(in[IN_D2E], -1, -1);
-                    }
-                    SlotMeta& mt = ring_meta[d * scope + (s % scope)];
+                    Range r;
+                    limits(in, r.lo, r.hi);
                     ++w_steps;
-                    if (lo > hi) {  // all inputs null: null step
-                        set_empty(mt);
-#pragma unroll
-                        for (int c = 0; c < 5; ++c) {
-                            so.lo[c] = 1;
-                            so.hi[c] = 0;
-                            so.ak[c] = INT_MIN;
-                        }
-                        so.endval = INT_MIN;
-                        return false;
-                    }
-                    if (lo < kmin_alloc || hi > kmax_alloc) {
+                    if (r.lo > r.hi) return r;
+                    if (r.lo < kmin_alloc || r.hi > kmax_alloc) {
                         status = ST_FAIL_WORKSPACE;
+                        return r;
+                    }
+                    if (status != ST_OK) return r;
+                    int out[5];
+                    out_offsets(d, slot, out);
+                    wf_cells<NT, BITS, TWO>(ws, in, out, r.lo, r.hi, d == 0 ? svd[0] : svd[1], k_end, d == 0 ? cend[0] : cend[1], red[d][red_i]);
+                    w_cells += (unsigned long long)(r.hi - r.lo + 1) * NCOMP;
+                    return r;
+                };
+                // after the barrier: trimmed ranges -> ring meta; returns END_REACHED of this wavefront
+                auto finish_dir = [&](int d, int slot, const Range& r) -> bool {
+                    SlotMeta& mt = ring_meta[d * ring_n + slot];
+                    if (r.lo > r.hi || status != ST_OK) {
+                        set_empty(mt);
                         return false;
                     }
-                    int* out[5];
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) out[c] = ring_ptr(d, s % scope, (TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M);
-                    wf_step<NT, BITS, TWO>(in, out, lo, hi, svd[d], k_end, cend[d], red[red_i], so);
-                    w_cells += (unsigned long long)(hi - lo + 1) * NCOMP;
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        mt.lo[c] = so.lo[c];
-                        mt.hi[c] = so.hi[c];
-                        mt.ak[c] = so.ak[c];
+                    StepOut so;
+                    wf_finish<TWO>(red[d][red_i], r.lo, r.hi, so);
+                    if (so.ambiguous) {
+                        int out[5];
+                        out_offsets(d, slot, out);
+                        wf_rescan<NT, TWO>(ws, out, r.lo, r.hi, plen, tlen, red[d][red_i], so);
                     }
-                    const int nxt = (red_i + 2) % 3;
-                    if (tid < NRED) red[nxt][tid] = INT_MIN;
-                    red_i = (red_i + 1) % 3;
-                    return end_reached(so, cend[d], k_end, tlen);
+                    store_meta(mt, so);
+                    return end_reached(so, d == 0 ? cend[0] : cend[1], k_end, tlen);
                 };
+                auto next_slot = [&](int slot) -> int { return slot + 1 == ring_n ? 0 : slot + 1; };
+
                 // wavefront_bialign_overlap: A0 = direction d0 at score s0, A1 = direction d1 at scores s1..s1-scope+1
                 auto overlap = [&](int d0, int d1, int s0, int s1) {
-                    const SlotMeta& m0 = ring_meta[d0 * scope + (s0 % scope)];
+                    const int slot0 = cur_slot[d0];
+                    const SlotMeta& m0 = ring_meta[d0 * ring_n + slot0];
                     const int kinv = tlen - plen;
-                    const int order[5] = {AW_COMP_D2, AW_COMP_I2, AW_COMP_D1, AW_COMP_I1, AW_COMP_M};
-                    for (int t = tid; t < scope * 5; t += NT) hitk[t] = INT_MAX;
-                    cta_sync<NT>();
                     const int bp_entry = bp.score;
-                    for (int i = 0; i < scope; ++i) {
-                        const int si = s1 - i;
-                        if (si < 0) break;
-                        const SlotMeta& m1 = ring_meta[d1 * scope + (si % scope)];
-#pragma unroll
-                        for (int oi = 0; oi < 5; ++oi) {
-                            const int c = order[oi];
-                            if (!TWO && (c == AW_COMP_D2 || c == AW_COMP_I2)) continue;
-                            const int credit = (c == AW_COMP_M) ? 0 : ((c == AW_COMP_D1 || c == AW_COMP_I1) ? pen.o1 : pen.o2);
-                            if (s0 + si - credit >= bp_entry) continue;
-                            if (m0.lo[c] > m0.hi[c] || m1.lo[c] > m1.hi[c]) continue;
-                            const int lo_1 = kinv - m1.hi[c], hi_1 = kinv - m1.lo[c];
-                            if (hi_1 < m0.lo[c] || m0.hi[c] < lo_1) continue;
-                            // necessary condition for any hit: antidiagonals must meet
-                            if ((long long)m0.ak[c] + (long long)m1.ak[c] < (long long)plen + tlen) continue;
-                            const int max_lo = max(m0.lo[c], lo_1), min_hi = min(m0.hi[c], hi_1);
-                            const int* p0 = ring_ptr(d0, s0 % scope, c);
-                            const int* p1 = ring_ptr(d1, si % scope, c);
-                            int best = INT_MAX;
-                            for (int k0 = max_lo + tid; k0 <= min_hi; k0 += NT) {
-                                const int k1 = kinv - k0;
-                                const int h0 = p0[k0], h1 = p1[k1];
-                                if (h0 + h1 >= tlen) {
-                                    if (c != AW_COMP_M) {  // indel2indel: the forward cell must be in bounds
-                                        const int kk = (d0 == 0) ? k0 : k1, hh = (d0 == 0) ? h0 : h1;
-                                        if (hh - kk > plen || hh > tlen) continue;
+                    // test t = i*5 + oi: reverse score s1-i, component order D2,I2,D1,I1,M
+                    auto test_comp = [](int oi) -> int { return oi == 0 ? AW_COMP_D2 : oi == 1 ? AW_COMP_I2 : oi == 2 ? AW_COMP_D1 : oi == 3 ? AW_COMP_I1 : AW_COMP_M; };
+                    auto credit_of = [&](int c) -> int { return (c == AW_COMP_M) ? 0 : ((c == AW_COMP_D1 || c == AW_COMP_I1) ? pen.o1 : pen.o2); };
+                    // candidate tests (gate + range intersection + antidiagonal bound), kept in order, by warp 0
+                    if (tid < 32) {
+                        int ncand = 0;
+                        const int ntests = min(scope, s1 + 1) * 5;
+                        for (int base = 0; base < ntests; base += 32) {
+                            const int t = base + tid;
+                            bool ok = false;
+                            if (t < ntests) {
+                                const int i = t / 5, oi = t - 5 * i, c = test_comp(oi);
+                                const int si = s1 - i;
+                                if (TWO || (c != AW_COMP_D2 && c != AW_COMP_I2)) {
+                                    const SlotMeta& m1 = ring_meta[d1 * ring_n + slot_back(cur_slot[d1], i)];
+                                    const int lo0 = m0.lo[c], hi0 = m0.hi[c], lo1 = kinv - m1.hi[c], hi1 = kinv - m1.lo[c];
+                                    ok = (s0 + si - credit_of(c) < bp_entry) && lo0 <= hi0 && m1.lo[c] <= m1.hi[c] && !(hi1 < lo0 || hi0 < lo1);
+                                    if (ok) {
+                                        const long long a0 = (c == AW_COMP_M) ? m0.akM : m0.akAll, a1 = (c == AW_COMP_M) ? m1.akM : m1.akAll;
+                                        ok = a0 + a1 >= (long long)plen + tlen;  // necessary for off0 + off1 >= tlen
                                     }
-                                    best = k0;
-                                    break;
                                 }
                             }
-                            best = __reduce_min_sync(0xffffffffu, best);
-                            if ((tid & 31) == 0 && best != INT_MAX) atomicMin(&hitk[i * 5 + oi], best);
+                            const unsigned mask = __ballot_sync(0xffffffffu, ok);
+                            if (ok) {
+                                const int pos = ncand + __popc(mask & ((1u << tid) - 1u));
+                                cand[pos] = t;
+                                hitk[pos] = INT_MAX;
+                            }
+                            ncand += __popc(mask);
                         }
+                        if (tid == 0) s_ncand = ncand;
                     }
                     cta_sync<NT>();
-                    // replay the tests in WFA2's order with the live breakpoint score
-                    for (int i = 0; i < scope; ++i) {
-                        const int si = s1 - i;
-                        if (si < 0) break;
-#pragma unroll
-                        for (int oi = 0; oi < 5; ++oi) {
-                            const int c = order[oi];
-                            if (!TWO && (c == AW_COMP_D2 || c == AW_COMP_I2)) continue;
-                            const int credit = (c == AW_COMP_M) ? 0 : ((c == AW_COMP_D1 || c == AW_COMP_I1) ? pen.o1 : pen.o2);
-                            if (s0 + si - credit >= bp.score) continue;
-                            const int k0 = hitk[i * 5 + oi];
-                            if (k0 == INT_MAX) continue;
+                    const int ncand = s_ncand;
+                    for (int j = 0; j < ncand; ++j) {
+                        const int t = cand[j], i = t / 5, c = test_comp(t - 5 * i);
+                        const int sl1 = slot_back(cur_slot[d1], i);
+                        const SlotMeta& m1 = ring_meta[d1 * ring_n + sl1];
+                        const int lo_1 = kinv - m1.hi[c], hi_1 = kinv - m1.lo[c];
+                        const int max_lo = max(m0.lo[c], lo_1), min_hi = min(m0.hi[c], hi_1);
+                        const int* p0 = ws + ring_off(d0, slot0, c);
+                        const int* p1 = ws + ring_off(d1, sl1, c);
+                        int best = INT_MAX;
+                        for (int k0 = max_lo + tid; k0 <= min_hi; k0 += NT) {
                             const int k1 = kinv - k0;
-                            const int h0 = ring_ptr(d0, s0 % scope, c)[k0], h1 = ring_ptr(d1, si % scope, c)[k1];
-                            if (d0 == 0) {
-                                bp.score_f = s0;
-                                bp.score_r = si;
-                                bp.k_f = k0;
-                                bp.off_f = h0;
-                            } else {
-                                bp.score_f = si;
-                                bp.score_r = s0;
-                                bp.k_f = k1;
-                                bp.off_f = h1;
+                            const int h0 = p0[k0], h1 = p1[k1];
+                            if (h0 + h1 >= tlen) {
+                                if (c != AW_COMP_M) {  // indel2indel: the forward cell must be in bounds
+                                    const int kk = (d0 == 0) ? k0 : k1, hh = (d0 == 0) ? h0 : h1;
+                                    if (hh - kk > plen || hh > tlen) continue;
+                                }
+                                best = k0;
+                                break;
                             }
-                            bp.score = s0 + si - credit;
-                            bp.comp = c;
                         }
+                        best = __reduce_min_sync(0xffffffffu, best);
+                        if ((tid & 31) == 0 && best != INT_MAX) atomicMin(&hitk[j], best);
                     }
-                    cta_sync<NT>();  // hitk is re-initialised by the next call
+                    cta_sync<NT>();
+                    // replay the candidate tests in WFA2's order with the live breakpoint score
+                    for (int j = 0; j < ncand; ++j) {
+                        const int k0 = hitk[j];
+                        if (k0 == INT_MAX) continue;
+                        const int t = cand[j], i = t / 5, c = test_comp(t - 5 * i);
+                        const int si = s1 - i, credit = credit_of(c);
+                        if (s0 + si - credit >= bp.score) continue;
+                        const int sl1 = slot_back(cur_slot[d1], i);
+                        const int k1 = kinv - k0;
+                        const int h0 = ws[ring_off(d0, slot0, c) + k0], h1 = ws[ring_off(d1, sl1, c) + k1];
+                        if (d0 == 0) {
+                            bp.score_f = s0;
+                            bp.score_r = si;
+                            bp.k_f = k0;
+                            bp.off_f = h0;
+                        } else {
+                            bp.score_f = si;
+                            bp.score_r = s0;
+                            bp.k_f = k1;
+                            bp.off_f = h1;
+                        }
+                        bp.score = s0 + si - credit;
+                        bp.comp = c;
+                    }
+                    cta_sync<NT>();  // cand/hitk are rewritten by the next call
                 };
 
                 StepOut so;
@@ -593,35 +849,66 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
                 bool fb_end = false;  // END_REACHED -> fall back to the base case
                 init_dir(0, so);
                 if (end_reached(so, cend[0], k_end, tlen)) fb_end = true;
-                f_ak = max(0, so.ak[AW_COMP_M]);
+                f_ak = max(0, so.akM);
                 if (!fb_end) {
                     init_dir(1, so);
                     if (end_reached(so, cend[1], k_end, tlen)) fb_end = true;
-                    r_ak = max(0, so.ak[AW_COMP_M]);
+                    r_ak = max(0, so.akM);
                 }
                 bool last_forward = false;
+                bool rev_pending = false;  // reverse wavefront score_r+1 already sits in slot next_slot(cur_slot[1])
                 const int max_antidiagonal = plen + tlen - 1;
+                bool rev_pending_done = false;  // END_REACHED flag of that speculative wavefront
+                lap(5);
+                // ---- phase 1: forward step s_f+1 and (speculative) reverse step s_r+1 share one barrier ----
                 while (!fb_end && status == ST_OK) {
                     if (f_ak + r_ak >= max_antidiagonal) break;
+                    const int slot_f = next_slot(cur_slot[0]), slot_r = next_slot(cur_slot[1]);
+                    const Range rf = launch_dir(0, score_f + 1, slot_f);
+                    const Range rr = launch_dir(1, score_r + 1, slot_r);
+                    cta_sync<NT>();
+                    bool done = finish_dir(0, slot_f, rf);
+                    const int akM_f = ring_meta[0 * ring_n + slot_f].akM;
+                    const bool done_r = finish_dir(1, slot_r, rr);
+                    const int akM_r = ring_meta[1 * ring_n + slot_r].akM;
+                    rotate_red();
+                    if (status != ST_OK) break;
+                    // commit forward
                     ++score_f;
-                    bool done = step_dir(0, score_f, so);
-                    f_ak = max(f_ak, max(0, done ? 0 : so.ak[AW_COMP_M]));
+                    cur_slot[0] = slot_f;
+                    f_ak = max(f_ak, max(0, done ? 0 : akM_f));
                     last_forward = true;
                     if (AW_BIALIGN_PHASE1_END_REACHED_RETURNS && done) {
                         fb_end = true;
                         break;
                     }
-                    if (status != ST_OK) break;
-                    if (f_ak + r_ak >= max_antidiagonal) break;
+                    if (f_ak + r_ak >= max_antidiagonal) {
+                        rev_pending = true;
+                        rev_pending_done = done_r;
+                        break;
+                    }
+                    // commit reverse
                     ++score_r;
-                    done = step_dir(1, score_r, so);
-                    r_ak = max(r_ak, max(0, done ? 0 : so.ak[AW_COMP_M]));
+                    cur_slot[1] = slot_r;
+                    r_ak = max(r_ak, max(0, done_r ? 0 : akM_r));
                     last_forward = false;
-                    if (AW_BIALIGN_PHASE1_END_REACHED_RETURNS && done) {
+                    if (AW_BIALIGN_PHASE1_END_REACHED_RETURNS && done_r) {
                         fb_end = true;
                         break;
                     }
                 }
+                lap(0);
+                // one committed step of direction d (phase 2): cells, barrier, finish
+                auto step_dir = [&](int d, int s) -> bool {
+                    const int slot = next_slot(cur_slot[d]);
+                    const Range r = launch_dir(d, s, slot);
+                    cta_sync<NT>();
+                    const bool done = finish_dir(d, slot, r);
+                    rotate_red();
+                    cur_slot[d] = slot;
+                    return done;
+                };
+                // ---- phase 2: advance until no better breakpoint is possible ----
                 const int gap_opening = TWO ? pen.o2 : pen.o1;
                 while (!fb_end && status == ST_OK) {
                     if (last_forward) {
@@ -629,7 +916,14 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
                         if (score_f + min_r - gap_opening >= bp.score) break;
                         overlap(0, 1, score_f, score_r);
                         ++score_r;
-                        const bool done = step_dir(1, score_r, so);
+                        bool done;
+                        if (rev_pending) {  // computed speculatively in phase 1
+                            rev_pending = false;
+                            cur_slot[1] = next_slot(cur_slot[1]);
+                            done = rev_pending_done;
+                        } else {
+                            done = step_dir(1, score_r);
+                        }
                         if (AW_BIALIGN_PHASE2_END_REACHED_RETURNS && done) {
                             fb_end = true;
                             break;
@@ -640,13 +934,14 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
                     if (min_f + score_r - gap_opening >= bp.score) break;
                     overlap(1, 0, score_r, score_f);
                     ++score_f;
-                    const bool done = step_dir(0, score_f, so);
+                    const bool done = step_dir(0, score_f);
                     if (AW_BIALIGN_PHASE2_END_REACHED_RETURNS && done) {
                         fb_end = true;
                         break;
                     }
                     last_forward = true;
                 }
+                lap(1);
                 if (status != ST_OK) break;
                 if (fb_end) {
                     do_base = true;
@@ -670,12 +965,11 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
             // =========== K7: wavefront_bialign_base: full-history WFA + backtrace ===========
             {
                 ++w_base;
+                lap(5);
                 const SeqView sv = SeqView{pw, tw, sp.pb, sp.tb, plen, tlen, false};
-                unsigned long long hist_used = 0;
-                auto hist_ptr = [&](unsigned off, int width, int clo, int c) -> int* {
-                    const int ci = TWO ? c : (c == AW_COMP_D1 ? 2 : c);
-                    return hist_base + off + (size_t)ci * width - clo;
-                };
+                long long hist_used = 0;
+                // component block of a history wavefront: element (c,k) at ws[hist_off(off,width,clo,c) + k]
+                auto hist_off = [&](int off, int width, int clo, int c) -> int { return hist_base + off + comp_idx(c) * width - clo; };
                 auto write_hist_meta = [&](int s, const SlotMeta& m) {
                     if (tid == 0) {
                         int* g = hist_meta + (size_t)s * HIST_META_INTS;
@@ -686,134 +980,114 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
                         }
                         g[10] = m.clo;
                         g[11] = m.width;
-                        g[12] = (int)m.off;
+                        g[12] = m.off;
                     }
                 };
+                auto slot_back = [&](int slot, int back) -> int {
+                    const int s = slot - back;
+                    return s < 0 ? s + ring_n : s;
+                };
                 StepOut so;
-                int score = 0;
+                int score = 0, slot = 0;
                 bool done;
                 {  // score 0
-                    int* r = red[red_i];
+                    int* r = red[0][red_i];
                     SlotMeta& mt = ring_meta[0];
                     if (tid == 0) {
                         int m = 0;
                         if (sp.cb == AW_COMP_M) m = extend_cell<BITS>(sv, 0, 0);
-                        hist_ptr(0, 1, 0, sp.cb)[0] = m;
-                        r[10 + sp.cb] = 2 * m;
-                        if (sp.cb == AW_COMP_M && sp.ce == AW_COMP_M && k_end == 0) r[15] = m;
+                        ws[hist_off(0, 1, 0, sp.cb)] = m;
+                        if (sp.cb == AW_COMP_M && sp.ce == AW_COMP_M && k_end == 0) r[RED_END] = m;
                     }
                     cta_sync<NT>();
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
-                        const bool on = (c == sp.cb);
-                        mt.lo[c] = so.lo[c] = on ? 0 : 1;
-                        mt.hi[c] = so.hi[c] = 0;
-                        mt.ak[c] = so.ak[c] = on ? r[10 + c] : INT_MIN;
+                        so.lo[c] = (c == sp.cb) ? 0 : 1;
+                        so.hi[c] = 0;
                     }
+                    so.akM = so.akAll = INT_MIN;
+                    so.endval = r[RED_END];
+                    so.ambiguous = false;
+                    store_meta(mt, so);
                     mt.clo = 0;
                     mt.width = 1;
                     mt.off = 0;
-                    so.endval = r[15];
                     hist_used = NCOMP;
                     write_hist_meta(0, mt);
-                    const int nxt = (red_i + 2) % 3;
-                    if (tid < NRED) red[nxt][tid] = INT_MIN;
-                    red_i = (red_i + 1) % 3;
+                    rotate_red();
                     done = end_reached(so, sp.ce, k_end, tlen);
                 }
                 while (!done) {
                     ++score;
+                    slot = (slot + 1 == ring_n) ? 0 : slot + 1;
                     if (score >= P.hist_max_scores) {
                         status = ST_FAIL_WORKSPACE;
                         break;
                     }
                     In in[7];
-                    auto fetch = [&](int c, int sc) -> In {
+                    auto fetch = [&](int c, int back) -> In {
                         In w;
-                        if (sc < 0) {
-                            w.p = nullptr;
+                        if (score - back < 0) {
+                            w.off = 0;
                             w.lo = 1;
                             w.hi = 0;
                             return w;
                         }
-                        const SlotMeta& m = ring_meta[sc % scope];
-                        w.p = hist_ptr(m.off, m.width, m.clo, c);
+                        const SlotMeta& m = ring_meta[slot_back(slot, back)];
+                        w.off = hist_off(m.off, m.width, m.clo, c);
                         w.lo = m.lo[c];
                         w.hi = m.hi[c];
                         return w;
                     };
-                    in[IN_MX] = fetch(AW_COMP_M, score - pen.x);
-                    in[IN_MO1] = fetch(AW_COMP_M, score - pen.o1 - pen.e1);
-                    in[IN_I1E] = fetch(AW_COMP_I1, score - pen.e1);
-                    in[IN_D1E] = fetch(AW_COMP_D1, score - pen.e1);
+                    in[IN_MX] = fetch(AW_COMP_M, pen.x);
+                    in[IN_MO1] = fetch(AW_COMP_M, pen.o1 + pen.e1);
+                    in[IN_I1E] = fetch(AW_COMP_I1, pen.e1);
+                    in[IN_D1E] = fetch(AW_COMP_D1, pen.e1);
                     if (TWO) {
-                        in[IN_MO2] = fetch(AW_COMP_M, score - pen.o2 - pen.e2);
-                        in[IN_I2E] = fetch(AW_COMP_I2, score - pen.e2);
-                        in[IN_D2E] = fetch(AW_COMP_D2, score - pen.e2);
+                        in[IN_MO2] = fetch(AW_COMP_M, pen.o2 + pen.e2);
+                        in[IN_I2E] = fetch(AW_COMP_I2, pen.e2);
+                        in[IN_D2E] = fetch(AW_COMP_D2, pen.e2);
                     } else {
-                        in[IN_MO2] = in[IN_I2E] = in[IN_D2E] = fetch(AW_COMP_M, -1);
+                        in[IN_MO2].off = in[IN_I2E].off = in[IN_D2E].off = 0;
+                        in[IN_MO2].lo = in[IN_I2E].lo = in[IN_D2E].lo = 1;
+                        in[IN_MO2].hi = in[IN_I2E].hi = in[IN_D2E].hi = 0;
                     }
-                    int lo = INT_MAX, hi = INT_MIN;
-                    auto lim = [&](const In& w, int dl, int dh) {
-                        if (w.lo <= w.hi) {
-                            lo = min(lo, w.lo + dl);
-                            hi = max(hi, w.hi + dh);
-                        }
-                    };
-                    lim(in[IN_MX], 0, 0);
-                    lim(in[IN_MO1], -1, 1);
-                    lim(in[IN_I1E], 1, 1);
-                    lim(in[IN_D1E], -1, -1);
-                    if (TWO) {
-                        lim(in[IN_MO2], -1, 1);
-                        lim(in[IN_I2E], 1, 1);
-                        lim(in[IN_D2E], -1, -1);
-                    }
-                    SlotMeta& mt = ring_meta[score % scope];
+                    int lo, hi;
+                    limits(in, lo, hi);
+                    SlotMeta& mt = ring_meta[slot];
                     ++w_steps;
                     if (lo > hi) {
-#pragma unroll
-                        for (int c = 0; c < 5; ++c) {
-                            mt.lo[c] = 1;
-                            mt.hi[c] = 0;
-                            mt.ak[c] = INT_MIN;
-                        }
-                        mt.clo = 0;
-                        mt.width = 0;
-                        mt.off = 0;
+                        set_empty(mt);
                         write_hist_meta(score, mt);
                         continue;
                     }
                     const int width = hi - lo + 1;
-                    if (hist_used + (unsigned long long)NCOMP * width > P.hist_ints_per_cta) {
+                    if (hist_used + (long long)NCOMP * width > (long long)P.hist_ints) {
                         status = ST_FAIL_WORKSPACE;
                         break;
                     }
-                    const unsigned off = (unsigned)hist_used;
-                    hist_used += (unsigned long long)NCOMP * width;
-                    int* out[5];
+                    const int off = (int)hist_used;
+                    hist_used += (long long)NCOMP * width;
+                    int out[5];
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) out[c] = hist_ptr(off, width, lo, (TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M);
-                    wf_step<NT, BITS, TWO>(in, out, lo, hi, sv, k_end, sp.ce, red[red_i], so);
+                    for (int c = 0; c < 5; ++c) out[c] = hist_off(off, width, lo, (TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M);
+                    wf_cells<NT, BITS, TWO>(ws, in, out, lo, hi, sv, k_end, sp.ce, red[0][red_i]);
+                    cta_sync<NT>();
+                    wf_finish<TWO>(red[0][red_i], lo, hi, so);
+                    if (so.ambiguous) wf_rescan<NT, TWO>(ws, out, lo, hi, plen, tlen, red[0][red_i], so);
                     w_cells += (unsigned long long)width * NCOMP;
-#pragma unroll
-                    for (int c = 0; c < 5; ++c) {
-                        mt.lo[c] = so.lo[c];
-                        mt.hi[c] = so.hi[c];
-                        mt.ak[c] = so.ak[c];
-                    }
+                    store_meta(mt, so);
                     mt.clo = lo;
                     mt.width = width;
                     mt.off = off;
                     write_hist_meta(score, mt);
-                    const int nxt = (red_i + 2) % 3;
-                    if (tid < NRED) red[nxt][tid] = INT_MIN;
-                    red_i = (red_i + 1) % 3;
+                    rotate_red();
                     done = end_reached(so, sp.ce, k_end, tlen);
                 }
                 if (status != ST_OK) break;
                 w_maxbase = max(w_maxbase, (unsigned)score);
                 cta_sync<NT>();  // history + meta visible to warp 0
+                lap(2);
 
                 // ---- wavefront_backtrace_affine by warp 0: lanes evaluate the candidates ----
                 unsigned n_leaf = 0;  // runs pushed (reverse order) into leaf_runs; uniform within warp 0
@@ -834,10 +1108,10 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
                     };
                     int type = sp.ce, sc = score, k = k_end, offset = tlen;
                     int v = plen, h = tlen;
-                    // candidate table: lane -> (bt type); cost / component / dk / add derive from it
+                    // lane l evaluates backtrace candidate type l+1 (AW_BT_*)
                     while (v > 0 && h > 0 && sc > 0) {
-                        const int bt = lane + 1;  // 1..9 for lanes 0..8
-                        int cand = INT_MIN;
+                        const int bt = lane + 1;
+                        int cand_v = INT_MIN;
                         if (lane < 9) {
                             int comp_src, cost, dk, add;
                             bool active;
@@ -857,12 +1131,12 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
                                 const int* g = hist_meta + (size_t)ss * HIST_META_INTS;
                                 const int kk = k + dk;
                                 if (g[comp_src] <= kk && kk <= g[5 + comp_src]) {
-                                    const int val = hist_ptr((unsigned)g[12], g[11], g[10], comp_src)[kk];
-                                    if (val >= 0) cand = ((val + add) << AW_BT_TYPE_BITS) | bt;
+                                    const int val = ws[hist_off(g[12], g[11], g[10], comp_src) + kk];
+                                    if (val >= 0) cand_v = ((val + add) << AW_BT_TYPE_BITS) | bt;
                                 }
                             }
                         }
-                        const int max_all = __reduce_max_sync(0xffffffffu, cand);
+                        const int max_all = __reduce_max_sync(0xffffffffu, cand_v);
                         if (max_all == INT_MIN) {  // cannot happen on a valid path
                             status = ST_FAIL_WORKSPACE;
                             break;
@@ -934,6 +1208,7 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
                 for (unsigned i = skip + tid; i < n_leaf; i += NT) pair_runs[base_n + i - skip] = leaf_runs[n_leaf - 1 - i];
                 if (tid == 0) s_nruns = base_n + n_leaf - skip;
                 cta_sync<NT>();
+                lap(3);
             }
         }  // DFS over sub-problems
 
@@ -1061,6 +1336,7 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
                 }
             }
         }
+        lap(4);
         if (tid == 0) {
             AwPairOut o;
             o.status = (status == ST_OK) ? AW_OK : AW_EWORKSPACE;
@@ -1081,6 +1357,7 @@ __global__ void __launch_bounds__(NT) aw_align_kernel(const KParams P) {
             o.n_breakpoints = w_bps;
             o.n_base = w_base;
             o.max_base_score = w_maxbase;
+            for (int i = 0; i < 6; ++i) o.cyc[i] = cyc[i];
             P.out[pair_i] = o;
         }
         cta_sync<NT>();

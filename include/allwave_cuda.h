@@ -137,6 +137,9 @@ int aw_batch_stats(aw_ctx* ctx, aw_batch* batch, uint64_t out[8]);
 /* device time of the dominant (alignment) kernel of the last launch, from CUDA events recorded
  * on the launch stream around that kernel alone; valid after aw_batch_fetch or a stream sync */
 int aw_batch_kernel_ms(aw_ctx* ctx, aw_batch* batch, float* out_ms);
+/* summed device clocks (thread 0 of each CTA) of the last fetched launch: [0] breakpoint phase 1,
+ * [1] phase 2 (overlap), [2] base-case wavefronts, [3] backtrace, [4] CIGAR/PAF emission, [5] other */
+int aw_batch_debug_cycles(aw_ctx* ctx, aw_batch* batch, uint64_t out[6]);
 void aw_batch_destroy(aw_ctx* ctx, aw_batch* batch);
 
 /* ---- orientation only: out_is_reverse[i] in {0,1} for each pair (AW_ORIENT_MASH) ---- */

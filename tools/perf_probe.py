@@ -21,5 +21,7 @@ for B in sizes:
     for it in range(2):
         t0 = time.time(); b.launch(); res = b.fetch(collect=False); t = time.time() - t0
         st = b.stats(); kms = b.kernel_ms()
+        dc = b.debug_cycles(); tot = max(1, sum(dc.values()))
+        print('   cycles%:', {k: round(100.0 * v / tot, 1) for k, v in dc.items()}, 'Mcyc/pair', round(tot / B / 1e6, 1))
         print(f"{cfg} B={B} it={it} wall={t:.3f}s kernel={kms:.1f}ms pairs/s={B/(kms/1e3):.1f} cells/s={st['cells']/(kms/1e3):.3e} steps={st['steps']} retried={st['pairs_retried']} failed={st['failed_pairs']} paf_bytes={st['paf_bytes']}")
     b.close()
