@@ -14,6 +14,9 @@
 #include "aw_common.cuh"
 #include "aw_sketch.cuh"
 #include "aw_wfa.cuh"
+#ifndef AW_ENABLE_BAND
+#define AW_ENABLE_BAND 0
+#endif
 
 static thread_local char g_err[512] = "";
 void aw_set_error(const char* fmt, ...) {
@@ -94,6 +97,8 @@ struct aw_ctx {
     int64_t max_w = 1 << 20;   // cap on allocated diagonals per wavefront (first attempt)
     int64_t hist_mb = 16;      // base-case history arena per CTA (first attempt)
     int64_t chunk_pairs = 65536;
+    int band_engine = 0;       // 1 = use the shared-memory diagonal-band engine for phase 1 (experimental)
+    int ws16 = 1;              // 1 = int16 wavefront storage when every offset fits
     // sequence store
     uint32_t n = 0;
     std::vector<uint64_t> lens;
@@ -228,11 +233,13 @@ extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
     std::string k(key);
     if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
     else if (k == "threads_per_cta") {
-        if (value != 0 && value != 32 && value != 128 && value != 256) return AW_EINVAL;
+        if (value != 0 && value != 32 && value != 256) return AW_EINVAL;
         c->threads_per_cta = (int)value;
     } else if (k == "max_wavefront_width") c->max_w = value;
     else if (k == "hist_mb") c->hist_mb = value;
     else if (k == "chunk_pairs") c->chunk_pairs = value > 0 ? value : 65536;
+    else if (k == "band_engine") c->band_engine = value ? 1 : 0;
+    else if (k == "ws16") c->ws16 = value ? 1 : 0;
     else return AW_EINVAL;
     return AW_OK;
 }
@@ -589,12 +596,14 @@ struct LaunchCfg {
     int nt, grid;
     int W;
     unsigned long long ws_ints, hist_ints, runs_cap;
+    long long ring16_off;
+    bool ws16;
     int hist_max_scores;
 };
 
-template <int NT, int BITS, bool TWO>
+template <int NT, int BITS, bool TWO, class WS>
 cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStream_t st) {
-    auto kern = awk::aw_align_kernel<NT, BITS, TWO>;
+    auto kern = awk::aw_align_kernel<NT, BITS, TWO, WS>;
     if (smem > 40 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -603,23 +612,24 @@ cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStrea
     return cudaGetLastError();
 }
 
-cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, int grid, cudaStream_t st) {
+cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bool ws16, int grid, cudaStream_t st) {
     const int scope = P.pen.scope;
-    const size_t smem = sizeof(awk::SlotMeta) * 2 * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt;
-#define AW_CASE(NT_, BITS_, TWO_) \
-    if (nt == NT_ && bits == BITS_ && two == TWO_) return launch_align<NT_, BITS_, TWO_>(P, grid, smem, st);
-    AW_CASE(32, 2, true)
-    AW_CASE(32, 2, false)
-    AW_CASE(32, 8, true)
-    AW_CASE(32, 8, false)
-    AW_CASE(128, 2, true)
-    AW_CASE(128, 2, false)
-    AW_CASE(128, 8, true)
-    AW_CASE(128, 8, false)
-    AW_CASE(256, 2, true)
-    AW_CASE(256, 2, false)
-    AW_CASE(256, 8, true)
-    AW_CASE(256, 8, false)
+    size_t smem = sizeof(awk::SlotMeta) * 2 * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt;
+    if (nt == 256 && P.ring16_int_off >= 0) smem += awk::band_smem_bytes(scope);  // band engine enabled
+#define AW_CASE(NT_, BITS_, TWO_, WS_, W16_) \
+    if (nt == NT_ && bits == BITS_ && two == TWO_ && ws16 == W16_) return launch_align<NT_, BITS_, TWO_, WS_>(P, grid, smem, st);
+    AW_CASE(32, 2, true, int, false)
+    AW_CASE(32, 2, false, int, false)
+    AW_CASE(32, 8, true, int, false)
+    AW_CASE(32, 8, false, int, false)
+    AW_CASE(256, 2, true, int, false)
+    AW_CASE(256, 2, false, int, false)
+    AW_CASE(256, 8, true, int, false)
+    AW_CASE(256, 8, false, int, false)
+    AW_CASE(256, 2, true, short, true)
+    AW_CASE(256, 2, false, short, true)
+    AW_CASE(256, 8, true, short, true)
+    AW_CASE(256, 8, false, short, true)
 #undef AW_CASE
     return cudaErrorInvalidValue;
 }
@@ -639,13 +649,20 @@ int plan_launch(aw_ctx* c, const aw_batch* b, uint64_t npairs, uint64_t max_p, u
     for (int a = 0; a < attempt; ++a) hist_ints *= 8;
     int hist_max_scores = attempt == 0 ? (nt == 32 ? 1024 : 4096) : (attempt == 1 ? 32768 : 262144);
     uint64_t runs_cap = max_p + max_t + 4;
-    uint64_t ring_ints = 2ull * (b->pen.scope + 1) * ncomp * W;
+    // int16 storage: every offset (incl. out-of-bounds I/D drift, <= 2*tlen+plen) must stay below 32000
+    const bool ws16 = c->ws16 && nt == 256 && (2 * max_t + max_p < 32000) && (2 * max_p + max_t < 32000);
+    const uint64_t epi = ws16 ? 2 : 1;  // elements per int
+    uint64_t ring_ints = (2ull * (b->pen.scope + 1) * ncomp * W + epi - 1) / epi;
     if (ring_ints >= 0x7f000000ull) {
         aw_set_error("wavefront ring of %llu ints per CTA exceeds the 32-bit workspace index", (unsigned long long)ring_ints);
         return AW_EUNSUPPORTED;
     }
     hist_ints = std::min<uint64_t>(hist_ints, 0x7ff00000ull - ring_ints);
-    uint64_t ws_ints = ring_ints + hist_ints;
+    // int16 band ring (NT=256 kernels): 2 x (scope + BAND_T + 2) slots x ncomp x W halfwords
+    uint64_t ring16_ints = (AW_ENABLE_BAND && c->band_engine && nt == 256 && b->pen.scope <= awk::BAND_MROWS) ? (2ull * (b->pen.scope + awk::BAND_T + 2) * ncomp * W + 1) / 2 + 8 : 0;
+    if (ring_ints + ring16_ints >= 0x7f000000ull) ring16_ints = 0;
+    hist_ints = std::min<uint64_t>(hist_ints, 0x7ff00000ull - ring_ints - ring16_ints);
+    uint64_t ws_ints = ring_ints + hist_ints + ring16_ints;
     uint64_t per_cta = ws_ints * 4 + (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 + runs_cap * 8;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return AW_ECUDA;
@@ -661,7 +678,9 @@ int plan_launch(aw_ctx* c, const aw_batch* b, uint64_t npairs, uint64_t max_p, u
     cfg->grid = (int)grid;
     cfg->W = (int)std::min<uint64_t>(W, 0x7ffffff0ull);
     cfg->ws_ints = ws_ints;
-    cfg->hist_ints = hist_ints;
+    cfg->ring16_off = ring16_ints ? (long long)(ring_ints + hist_ints) : -1;
+    cfg->hist_ints = hist_ints * epi;  // capacity in workspace elements
+    cfg->ws16 = ws16;
     cfg->runs_cap = runs_cap;
     cfg->hist_max_scores = hist_max_scores;
     int rc;
@@ -685,7 +704,8 @@ void fill_params(aw_ctx* c, aw_batch* b, const LaunchCfg& cfg, awk::KParams* P) 
     P->ws = c->ws_main.as<int>();
     P->ws_ints_per_cta = cfg.ws_ints;
     P->W = cfg.W;
-    P->hist_ints = (int)cfg.hist_ints;
+    P->hist_ints = (int)std::min<unsigned long long>(cfg.hist_ints, 0x7fffffffull);
+    P->ring16_int_off = cfg.ring16_off;
     P->ws_hist_meta = c->ws_hist_meta.as<int>();
     P->hist_max_scores = cfg.hist_max_scores;
     P->ws_runs = c->ws_runs.as<uint32_t>();
@@ -734,7 +754,7 @@ extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
         AW_CUDA_CHECK(cudaEventCreate(&b->ev1));
     }
     AW_CUDA_CHECK(cudaEventRecord(b->ev0, st));
-    cudaError_t e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.grid, st);
+    cudaError_t e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.ws16, cfg.grid, st);
     if (e != cudaSuccess) {
         aw_set_error("align kernel launch (nt=%d grid=%d): %s", cfg.nt, cfg.grid, cudaGetErrorString(e));
         return AW_ECUDA;
@@ -784,7 +804,7 @@ static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
         P.bytes = d_bytes.as<uint8_t>();
         P.bytes_cursor = d_ctl.as<unsigned long long>() + 1;
         P.bytes_cap = bytes_cap;
-        if (e == cudaSuccess) e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.grid, c->stream);
+        if (e == cudaSuccess) e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.ws16, cfg.grid, c->stream);
         ++b->stats[0];
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         std::vector<AwPairOut> outs(b->npairs);

@@ -19,7 +19,23 @@ constexpr int NRED = 16;       // reduction slots, see RED_* below
 constexpr int MAX_STACK = 96;  // DFS depth bound of the biWFA recursion
 constexpr int HIST_META_INTS = 16;
 constexpr int EDGE_ZONE = 64;  // I/D in-bounds tracking is only done this close to a wavefront end
-constexpr int SEQ_SMEM_WORDS = 4096;  // 16 KB of shared memory for the pair's packed sequences (guards included)
+constexpr int SEQ_SMEM_WORDS = 2048;  // 8 KB of shared memory for the pair's packed sequences (guards included)
+// ---- shared-memory diagonal-band engine (phase 1 of the breakpoint search) ----
+constexpr int BAND_T = 32;            // scores advanced per band without leaving shared memory
+constexpr int BAND_WP = 1024;         // diagonals held per tile (output range + BAND_T halo either side)
+constexpr int BAND_WT = BAND_WP - 2 * BAND_T;
+constexpr int BAND_MROWS = 27;        // M history rows (max_score_scope <= 27)
+constexpr int BAND_ROWS = BAND_MROWS + 3 + 3 + 2 + 2 + 1;  // + I1, D1, I2, D2 windows + one all-NULL row
+constexpr int BAND_NULL_ROW = BAND_ROWS - 1;
+constexpr int BAND_TAB = 13;          // per-step table: RED_* layout
+constexpr int BAND_MIN_SCORE = 600;   // sub-problems expected to score less use the generic path
+constexpr short NULL16 = -16384;
+struct Meta16 {
+    int lo[5], hi[5], akM, akAll;
+};
+__host__ __device__ constexpr size_t band_smem_bytes(int scope) {
+    return sizeof(short) * BAND_ROWS * BAND_WP + sizeof(int) * 2 * (BAND_T + 1) * BAND_TAB + sizeof(Meta16) * 2 * (scope + BAND_T + 2) + 16;
+}
 
 enum { IN_MX = 0, IN_MO1, IN_I1E, IN_D1E, IN_MO2, IN_I2E, IN_D2E };
 enum { ST_OK = 0, ST_END_REACHED = 1, ST_FAIL_WORKSPACE = 2 };
@@ -70,6 +86,7 @@ struct KParams {
     unsigned long long ws_ints_per_cta;
     int W;                   // allocated diagonals per ring wavefront
     int hist_ints;           // history arena size (ints)
+    long long ring16_int_off; // int offset inside the CTA workspace of the int16 band ring (2 x (scope+BAND_T+2) x ncomp x W halfwords), or -1
     int* ws_hist_meta;       // [cta][hist_max_scores][HIST_META_INTS]
     int hist_max_scores;
     uint32_t* ws_runs;       // [cta][2][runs_cap]: pair runs, then leaf scratch
@@ -165,7 +182,45 @@ __device__ __forceinline__ int extend_cell(const SeqView& s, int k, int off) {
     return off + n;
 }
 
-__device__ __forceinline__ int ld_in(const int* __restrict__ ws, const In& w, int k) { return (k >= w.lo && k <= w.hi) ? ws[w.off + k] : AW_NULLV; }
+// first (branch-free) round of the match extension: up to one word of symbols.  `more` is set
+// when the whole word matched and symbols remain (the caller continues with lcp_fwd/lcp_rev).
+template <int BITS>
+__device__ __forceinline__ void extend_first(const SeqView& s, int k, int off, int& n, bool& more) {
+    constexpr int SPW = 32 / BITS;
+    int v = off - k, h = off;
+    const int maxlen = min(s.plen - v, s.tlen - h);
+    if (maxlen <= 0) v = h = 0;  // nothing to compare: keep the (unused) loads inside the sequences
+    uint32_t x;
+    int cnt;
+    if (s.rev) {
+        x = load_rev<BITS>(s.pw, s.p0 - v) ^ load_rev<BITS>(s.tw, s.t0 - h);
+        cnt = __clz(x) / BITS;  // clz(0) = 32 -> SPW
+    } else {
+        x = load_fwd<BITS>(s.pw, s.p0 + v) ^ load_fwd<BITS>(s.tw, s.t0 + h);
+        cnt = x ? (__ffs(x) - 1) / BITS : SPW;
+    }
+    n = max(0, min(cnt, maxlen));
+    more = (x == 0) && (maxlen > SPW);
+}
+template <int BITS>
+__device__ __forceinline__ int extend_rest(const SeqView& s, int k, int off) {  // off already advanced by one word
+    constexpr int SPW = 32 / BITS;
+    const int v = off - k, h = off;
+    const int maxlen = min(s.plen - v, s.tlen - h);
+    if (maxlen <= 0) return off;
+    const int n = s.rev ? lcp_rev<BITS>(s.pw, s.p0 - v, s.tw, s.t0 - h, maxlen) : lcp_fwd<BITS>(s.pw, s.p0 + v, s.tw, s.t0 + h, maxlen);
+    (void)SPW;
+    return off + n;
+}
+
+// workspace element type: int (any length) or short (offsets < 32000; halves the L2/HBM footprint).
+// Every negative offset means "null", so the int16 form stores one canonical negative value.
+template <class WS>
+__device__ __forceinline__ WS to_ws(int v);
+template <>
+__device__ __forceinline__ int to_ws<int>(int v) { return v; }
+template <>
+__device__ __forceinline__ short to_ws<short>(int v) { return (short)(v < 0 ? (int)NULL16 : v); }
 
 struct StepOut {
     int lo[5], hi[5];
@@ -178,8 +233,8 @@ struct StepOut {
 // reductions (trim ends, antidiagonal bounds, end-cell value) into `red`.  No barrier here.
 // Restates wavefront_compute_affine2p_idm + wavefront_extend_matches_packed_end2end(_max)
 // (SURVEY A.2, A.3).  `red` must hold INT_MIN on entry.
-template <int NT, int BITS, bool TWO>
-__device__ __forceinline__ void wf_cells(int* __restrict__ ws, const In (&in)[7], const int (&out)[5], int lo, int hi, const SeqView& sv, int k_end,
+template <int NT, int BITS, bool TWO, class WS>
+__device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7], const int (&out)[5], int lo, int hi, const SeqView& sv, int k_end,
                                          int comp_end, int* red) {
     const int tid = threadIdx.x;
     const unsigned tlen = (unsigned)sv.tlen, plen = (unsigned)sv.plen;
@@ -206,18 +261,18 @@ __device__ __forceinline__ void wf_cells(int* __restrict__ ws, const In (&in)[7]
     // running pointers: one per input / output array, advanced by NT per iteration, so the loop
     // body addresses everything with immediate offsets (no per-access 64-bit arithmetic)
     const int k0 = lo + tid;
-    const int* p_mx = ws + in[IN_MX].off + k0;
-    const int* p_mo1 = ws + in[IN_MO1].off + k0;
-    const int* p_i1e = ws + in[IN_I1E].off + k0;
-    const int* p_d1e = ws + in[IN_D1E].off + k0;
-    const int* p_mo2 = ws + in[IN_MO2].off + k0;
-    const int* p_i2e = ws + in[IN_I2E].off + k0;
-    const int* p_d2e = ws + in[IN_D2E].off + k0;
-    int* q_m = ws + out[AW_COMP_M] + k0;
-    int* q_i1 = ws + out[AW_COMP_I1] + k0;
-    int* q_d1 = ws + out[AW_COMP_D1] + k0;
-    int* q_i2 = ws + out[AW_COMP_I2] + k0;
-    int* q_d2 = ws + out[AW_COMP_D2] + k0;
+    const WS* p_mx = ws + in[IN_MX].off + k0;
+    const WS* p_mo1 = ws + in[IN_MO1].off + k0;
+    const WS* p_i1e = ws + in[IN_I1E].off + k0;
+    const WS* p_d1e = ws + in[IN_D1E].off + k0;
+    const WS* p_mo2 = ws + in[IN_MO2].off + k0;
+    const WS* p_i2e = ws + in[IN_I2E].off + k0;
+    const WS* p_d2e = ws + in[IN_D2E].off + k0;
+    WS* q_m = ws + out[AW_COMP_M] + k0;
+    WS* q_i1 = ws + out[AW_COMP_I1] + k0;
+    WS* q_d1 = ws + out[AW_COMP_D1] + k0;
+    WS* q_i2 = ws + out[AW_COMP_I2] + k0;
+    WS* q_d2 = ws + out[AW_COMP_D2] + k0;
     // one cell: recurrences, bounds, extend, stores, trim / antidiagonal tracking
     auto cell = [&](int k, int j, int mo1l, int mo1r, int i1l, int d1r, int mo2l, int mo2r, int i2l, int d2r, int mx) {
         const int i1 = max(mo1l, i1l) + 1;
@@ -238,12 +293,12 @@ __device__ __forceinline__ void wf_cells(int* __restrict__ ws, const In (&in)[7]
             m_hi = k;
             akM = max(akM, 2 * m - k);
         }
-        q_m[j * NT] = m;
-        q_i1[j * NT] = i1;
-        q_d1[j * NT] = d1;
+        q_m[j * NT] = to_ws<WS>(m);
+        q_i1[j * NT] = to_ws<WS>(i1);
+        q_d1[j * NT] = to_ws<WS>(d1);
         if (TWO) {
-            q_i2[j * NT] = i2;
-            q_d2[j * NT] = d2;
+            q_i2[j * NT] = to_ws<WS>(i2);
+            q_d2[j * NT] = to_ws<WS>(d2);
         }
         if (narrow || k - lo < EDGE_ZONE || hi - k < EDGE_ZONE) {
             // wavefront_compute_trim_ends keeps [first, last] in-bounds cell of every component
@@ -284,45 +339,35 @@ __device__ __forceinline__ void wf_cells(int* __restrict__ ws, const In (&in)[7]
             q_d2 += n;
         }
     };
-    constexpr int J = 4;  // cells per thread whose global loads are issued back to back
     int k = k0;
-    // batched interior: all J cells of this thread are unchecked, 9*J loads in flight at once
-    while (k >= fast_lo && k + (J - 1) * NT <= fast_hi && k + (J - 1) * NT <= hi) {
-        int a[J][9];
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-            a[j][0] = p_mo1[j * NT - 1];
-            a[j][1] = p_mo1[j * NT + 1];
-            a[j][2] = p_i1e[j * NT - 1];
-            a[j][3] = p_d1e[j * NT + 1];
-            if (TWO) {
-                a[j][4] = p_mo2[j * NT - 1];
-                a[j][5] = p_mo2[j * NT + 1];
-                a[j][6] = p_i2e[j * NT - 1];
-                a[j][7] = p_d2e[j * NT + 1];
-            } else {
-                a[j][4] = a[j][5] = a[j][6] = a[j][7] = AW_NULLV;
-            }
-            a[j][8] = p_mx[j * NT];
-        }
-#pragma unroll
-        for (int j = 0; j < J; ++j) cell(k + j * NT, j, a[j][0], a[j][1], a[j][2], a[j][3], a[j][4], a[j][5], a[j][6], a[j][7], a[j][8]);
-        k += J * NT;
-        advance(J * NT);
-    }
-    // edges and remainders: one checked cell at a time
     for (; k <= hi; k += NT) {
-        auto ck = [&](const In& w, const int* p, int d) -> int { return (k + d >= w.lo && k + d <= w.hi) ? p[d] : AW_NULLV; };
-        const int mo1l = ck(in[IN_MO1], p_mo1, -1), mo1r = ck(in[IN_MO1], p_mo1, 1);
-        const int i1l = ck(in[IN_I1E], p_i1e, -1), d1r = ck(in[IN_D1E], p_d1e, 1);
-        int mo2l = AW_NULLV, mo2r = AW_NULLV, i2l = AW_NULLV, d2r = AW_NULLV;
-        if (TWO) {
-            mo2l = ck(in[IN_MO2], p_mo2, -1);
-            mo2r = ck(in[IN_MO2], p_mo2, 1);
-            i2l = ck(in[IN_I2E], p_i2e, -1);
-            d2r = ck(in[IN_D2E], p_d2e, 1);
+        int mo1l, mo1r, i1l, d1r, mo2l = AW_NULLV, mo2r = AW_NULLV, i2l = AW_NULLV, d2r = AW_NULLV, mx;
+        if (k >= fast_lo && k <= fast_hi) {  // interior: immediate-offset loads, no checks
+            mo1l = p_mo1[-1];
+            mo1r = p_mo1[1];
+            i1l = p_i1e[-1];
+            d1r = p_d1e[1];
+            if (TWO) {
+                mo2l = p_mo2[-1];
+                mo2r = p_mo2[1];
+                i2l = p_i2e[-1];
+                d2r = p_d2e[1];
+            }
+            mx = p_mx[0];
+        } else {
+            auto ck = [&](const In& w, const WS* p, int d) -> int { return (k + d >= w.lo && k + d <= w.hi) ? (int)p[d] : AW_NULLV; };
+            mo1l = ck(in[IN_MO1], p_mo1, -1);
+            mo1r = ck(in[IN_MO1], p_mo1, 1);
+            i1l = ck(in[IN_I1E], p_i1e, -1);
+            d1r = ck(in[IN_D1E], p_d1e, 1);
+            if (TWO) {
+                mo2l = ck(in[IN_MO2], p_mo2, -1);
+                mo2r = ck(in[IN_MO2], p_mo2, 1);
+                i2l = ck(in[IN_I2E], p_i2e, -1);
+                d2r = ck(in[IN_D2E], p_d2e, 1);
+            }
+            mx = ck(in[IN_MX], p_mx, 0);
         }
-        const int mx = ck(in[IN_MX], p_mx, 0);
         cell(k, 0, mo1l, mo1r, i1l, d1r, mo2l, mo2r, i2l, d2r, mx);
         advance(NT);
     }
@@ -373,8 +418,8 @@ __device__ __forceinline__ void wf_finish(const int* red, int lo, int hi, StepOu
 }
 
 // exact trim of every I/D component by re-reading the stored wavefront (rare slow path)
-template <int NT, bool TWO>
-__device__ __noinline__ void wf_rescan(const int* __restrict__ ws, const int (&out)[5], int lo, int hi, int plen_, int tlen_, int* red, StepOut& so) {
+template <int NT, bool TWO, class WS>
+__device__ __noinline__ void wf_rescan(const WS* __restrict__ ws, const int (&out)[5], int lo, int hi, int plen_, int tlen_, int* red, StepOut& so) {
     const unsigned tlen = (unsigned)tlen_, plen = (unsigned)plen_;
     cta_sync<NT>();
     if (threadIdx.x < NRED) red[threadIdx.x] = INT_MIN;
@@ -480,7 +525,7 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
-template <int NT, int BITS, bool TWO>
+template <int NT, int BITS, bool TWO, class WS>
 __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_align_kernel(const KParams P) {
     constexpr int NCOMP = TWO ? 5 : 3;
     extern __shared__ unsigned long long smem_raw[];
@@ -490,6 +535,15 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
     int* cand = reinterpret_cast<int*>(ring_meta + 2 * ring_n);                                     // [scope*5] candidate tests
     int* hitk = cand + scope * 5;                                                                    // [scope*5] first hit per candidate
     unsigned long long* scanbuf = reinterpret_cast<unsigned long long*>(hitk + scope * 5);  // [NT]; 8-byte aligned: 60*2*ring_n + 40*scope
+#ifndef AW_ENABLE_BAND
+#define AW_ENABLE_BAND 0  // the shared-memory diagonal-band engine is experimental: measured slower than the generic loop
+#endif
+    constexpr bool BAND = (NT == 256) && (AW_ENABLE_BAND != 0);
+    const int rn16 = scope + BAND_T + 2;  // slots of the int16 band ring
+    short* band_rows = reinterpret_cast<short*>(scanbuf + NT);                    // [BAND_ROWS][BAND_WP]
+    int* band_tab = reinterpret_cast<int*>(band_rows + BAND_ROWS * BAND_WP);      // [2][BAND_T+1][BAND_TAB]
+    Meta16* meta16 = reinterpret_cast<Meta16*>(band_tab + 2 * (BAND_T + 1) * BAND_TAB);  // [2][rn16]
+    __shared__ int s_band_flag;
     __shared__ int red[2][3][NRED];
     __shared__ SubProblem stack[MAX_STACK];
     __shared__ unsigned s_next;
@@ -501,7 +555,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
 
     const int tid = threadIdx.x;
     const AwPen pen = P.pen;
-    int* const ws = P.ws + (size_t)blockIdx.x * P.ws_ints_per_cta;
+    int* const ws_i = P.ws + (size_t)blockIdx.x * P.ws_ints_per_cta;
+    WS* const ws = reinterpret_cast<WS*>(ws_i);  // all wavefront offsets below are in WS elements
     const int W = P.W;
     const int hist_base = 2 * ring_n * NCOMP * W;  // history arena starts after the rings
     int* const hist_meta = P.ws_hist_meta + (size_t)blockIdx.x * (size_t)P.hist_max_scores * HIST_META_INTS;
@@ -659,7 +714,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
                     if (tid == 0) {
                         int m = 0;
                         if (cbeg[d] == AW_COMP_M) m = extend_cell<BITS>(svd[d], 0, 0);
-                        ws[ring_off(d, 0, cbeg[d])] = m;
+                        ws[ring_off(d, 0, cbeg[d])] = to_ws<WS>(m);
                         r[RED_AKM] = (cbeg[d] == AW_COMP_M) ? 2 * m : INT_MIN;
                         r[RED_AKALL] = 2 * m;
                         if (cbeg[d] == AW_COMP_M && cend[d] == AW_COMP_M && k_end == 0) r[RED_END] = m;
@@ -728,7 +783,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
                     if (status != ST_OK) return r;
                     int out[5];
                     out_offsets(d, slot, out);
-                    wf_cells<NT, BITS, TWO>(ws, in, out, r.lo, r.hi, d == 0 ? svd[0] : svd[1], k_end, d == 0 ? cend[0] : cend[1], red[d][red_i]);
+                    wf_cells<NT, BITS, TWO, WS>(ws, in, out, r.lo, r.hi, d == 0 ? svd[0] : svd[1], k_end, d == 0 ? cend[0] : cend[1], red[d][red_i]);
                     w_cells += (unsigned long long)(r.hi - r.lo + 1) * NCOMP;
                     return r;
                 };
@@ -744,7 +799,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
                     if (so.ambiguous) {
                         int out[5];
                         out_offsets(d, slot, out);
-                        wf_rescan<NT, TWO>(ws, out, r.lo, r.hi, plen, tlen, red[d][red_i], so);
+                        wf_rescan<NT, TWO, WS>(ws, out, r.lo, r.hi, plen, tlen, red[d][red_i], so);
                     }
                     store_meta(mt, so);
                     return end_reached(so, d == 0 ? cend[0] : cend[1], k_end, tlen);
@@ -798,8 +853,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
                         const SlotMeta& m1 = ring_meta[d1 * ring_n + sl1];
                         const int lo_1 = kinv - m1.hi[c], hi_1 = kinv - m1.lo[c];
                         const int max_lo = max(m0.lo[c], lo_1), min_hi = min(m0.hi[c], hi_1);
-                        const int* p0 = ws + ring_off(d0, slot0, c);
-                        const int* p1 = ws + ring_off(d1, sl1, c);
+                        const WS* p0 = ws + ring_off(d0, slot0, c);
+                        const WS* p1 = ws + ring_off(d1, sl1, c);
                         int best = INT_MAX;
                         for (int k0 = max_lo + tid; k0 <= min_hi; k0 += NT) {
                             const int k1 = kinv - k0;
@@ -859,9 +914,371 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
                 bool rev_pending = false;  // reverse wavefront score_r+1 already sits in slot next_slot(cur_slot[1])
                 const int max_antidiagonal = plen + tlen - 1;
                 bool rev_pending_done = false;  // END_REACHED flag of that speculative wavefront
-                lap(5);
+                lap(4);
+                // =========== shared-memory diagonal-band engine for phase 1 ===========
+                // Advances both directions BAND_T scores at a time inside shared memory (int16 offsets,
+                // NULL-filled halos, no range checks, one barrier per step), streams every produced row to
+                // an int16 ring in global memory, then replays WFA2's alternation over the per-step table
+                // to find the exact break.  Anything it cannot resolve locally (an out-of-bounds positive
+                // I/D offset, whose trimming depends on the whole row) aborts the band: the generic loop
+                // below then redoes phase 1 from score 0.  Hand-over converts the last `scope` rows to the
+                // generic int32 ring so that phase 2 (overlap) runs on the proven path.
+                bool band_done = false;
+                if constexpr (BAND)
+                if (!fb_end && P.ring16_int_off >= 0 && scope <= BAND_MROWS && pen.e1 <= 2 && (!TWO || pen.e2 <= 1) && sp.rem > BAND_MIN_SCORE &&
+                    2 * tlen + plen < 32000 && 2 * plen + tlen < 32000) {
+                    short* const ring16 = reinterpret_cast<short*>(ws_i + P.ring16_int_off);
+                    auto r16_off = [&](int d, int slot, int c) -> long long { return ((long long)((d * rn16 + slot) * NCOMP + comp_idx(c))) * W + koff; };
+                    // row 0 of both directions (written by init_dir) -> int16 ring + meta
+                    if (tid < 2) {
+                        const int d = tid;
+                        ring16[r16_off(d, 0, cbeg[d])] = (short)ws[ring_off(d, 0, cbeg[d])];
+                    }
+                    for (int d = 0; d < 2; ++d) {
+                        const SlotMeta& m = ring_meta[d * ring_n + 0];
+                        Meta16& q = meta16[d * rn16 + 0];
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) {
+                            q.lo[c] = m.lo[c];
+                            q.hi[c] = m.hi[c];
+                        }
+                        q.akM = m.akM;
+                        q.akAll = m.akAll;
+                    }
+                    if (tid == 0) s_band_flag = 0;
+                    cta_sync<NT>();
+                    int S = 0;        // both directions are complete up to score S
+                    int slotS = 0;    // int16 ring slot of score S
+                    bool band_fail = false, band_break = false;
+                    // smem row of a score (negative score -> the all-NULL row)
+                    auto row_of = [&](int base, int mod, int cur, int back, int s) -> int {
+                        if (s - back < 0) return BAND_NULL_ROW;
+                        int r = cur - back;
+                        if (r < 0) r += mod;
+                        return base + r;
+                    };
+                    // all-NULL row
+                    for (int i = tid; i < BAND_WP; i += NT) band_rows[BAND_NULL_ROW * BAND_WP + i] = NULL16;
+                    while (!band_fail && !band_break && !fb_end) {
+                        if (f_ak + r_ak >= max_antidiagonal) {
+                            band_break = true;
+                            break;
+                        }
+                        // ---- per-step table ----
+                        for (int i = tid; i < 2 * (BAND_T + 1) * BAND_TAB; i += NT) band_tab[i] = INT_MIN;
+                        cta_sync<NT>();
+                        const int m27 = S % BAND_MROWS, m3 = S % 3, m2 = S % 2;
+                        for (int d = 0; d < 2; ++d) {
+                            const SeqView& sv = (d == 0) ? svd[0] : svd[1];
+                            const int ce = (d == 0) ? cend[0] : cend[1];
+                            // span of the history rows, widened by the band length
+                            int mn = INT_MAX, mxk = INT_MIN;
+                            for (int j = 0; j < scope && S - j >= 0; ++j) {
+                                int sl = slotS - j;
+                                if (sl < 0) sl += rn16;
+                                const Meta16& q = meta16[d * rn16 + sl];
+#pragma unroll
+                                for (int c = 0; c < 5; ++c)
+                                    if (q.lo[c] <= q.hi[c]) {
+                                        mn = min(mn, q.lo[c]);
+                                        mxk = max(mxk, q.hi[c]);
+                                    }
+                            }
+                            if (mn > mxk) {  // every history row is empty: cannot happen in exact mode
+                                band_fail = true;
+                                break;
+                            }
+                            const int span_lo = mn - BAND_T, span_hi = mxk + BAND_T;
+                            for (int ka = span_lo; ka <= span_hi; ka += BAND_WT) {
+                                const int kb = min(ka + BAND_WT - 1, span_hi);
+                                const int base_k = ka - BAND_T;  // diagonal of shared-memory column 0
+                                // ---- load the history window (NULL outside each row's trimmed range) ----
+                                auto load_row = [&](int row, int c, int score) {
+                                    short* dst = band_rows + row * BAND_WP;
+                                    int lo_r = 1, hi_r = 0;
+                                    const short* src = ring16;
+                                    if (score >= 0) {
+                                        int sl = slotS - (S - score);
+                                        if (sl < 0) sl += rn16;
+                                        const Meta16& q = meta16[d * rn16 + sl];
+                                        lo_r = q.lo[c];
+                                        hi_r = q.hi[c];
+                                        src = ring16 + r16_off(d, sl, c);
+                                    }
+                                    for (int i = tid; i < BAND_WP; i += NT) {
+                                        const int k = base_k + i;
+                                        dst[i] = (k >= lo_r && k <= hi_r) ? src[k] : NULL16;
+                                    }
+                                };
+                                for (int j = 0; j < BAND_MROWS - 1; ++j) {
+                                    int r = m27 - j;
+                                    if (r < 0) r += BAND_MROWS;
+                                    load_row(r, AW_COMP_M, S - j);
+                                }
+                                for (int j = 0; j < 2; ++j) {
+                                    int r = m3 - j;
+                                    if (r < 0) r += 3;
+                                    load_row(BAND_MROWS + r, AW_COMP_I1, S - j);
+                                    load_row(BAND_MROWS + 3 + r, AW_COMP_D1, S - j);
+                                }
+                                if (TWO) {
+                                    load_row(BAND_MROWS + 6 + m2, AW_COMP_I2, S);
+                                    load_row(BAND_MROWS + 8 + m2, AW_COMP_D2, S);
+                                }
+                                cta_sync<NT>();
+                                // ---- BAND_T steps inside shared memory ----
+                                int c27 = m27, c3 = m3, c2 = m2, sl16 = slotS;
+                                for (int t = 1; t <= BAND_T; ++t) {
+                                    const int s = S + t;
+                                    c27 = (c27 + 1 == BAND_MROWS) ? 0 : c27 + 1;
+                                    c3 = (c3 + 1 == 3) ? 0 : c3 + 1;
+                                    c2 ^= 1;
+                                    sl16 = (sl16 + 1 == rn16) ? 0 : sl16 + 1;
+                                    const short* r_mx = band_rows + row_of(0, BAND_MROWS, c27, pen.x, s) * BAND_WP;
+                                    const short* r_mo1 = band_rows + row_of(0, BAND_MROWS, c27, pen.o1 + pen.e1, s) * BAND_WP;
+                                    const short* r_i1 = band_rows + row_of(BAND_MROWS, 3, c3, pen.e1, s) * BAND_WP;
+                                    const short* r_d1 = band_rows + row_of(BAND_MROWS + 3, 3, c3, pen.e1, s) * BAND_WP;
+                                    const short* r_mo2 = band_rows + (TWO ? row_of(0, BAND_MROWS, c27, pen.o2 + pen.e2, s) : BAND_NULL_ROW) * BAND_WP;
+                                    const short* r_i2 = band_rows + (TWO ? row_of(BAND_MROWS + 6, 2, c2, pen.e2, s) : BAND_NULL_ROW) * BAND_WP;
+                                    const short* r_d2 = band_rows + (TWO ? row_of(BAND_MROWS + 8, 2, c2, pen.e2, s) : BAND_NULL_ROW) * BAND_WP;
+                                    short* w_m = band_rows + c27 * BAND_WP;
+                                    short* w_i1 = band_rows + (BAND_MROWS + c3) * BAND_WP;
+                                    short* w_d1 = band_rows + (BAND_MROWS + 3 + c3) * BAND_WP;
+                                    short* w_i2 = band_rows + (BAND_MROWS + 6 + c2) * BAND_WP;
+                                    short* w_d2 = band_rows + (BAND_MROWS + 8 + c2) * BAND_WP;
+                                    short* g_m = ring16 + r16_off(d, sl16, AW_COMP_M);
+                                    short* g_i1 = ring16 + r16_off(d, sl16, AW_COMP_I1);
+                                    short* g_d1 = ring16 + r16_off(d, sl16, AW_COMP_D1);
+                                    short* g_i2 = ring16 + r16_off(d, sl16, TWO ? AW_COMP_I2 : AW_COMP_M);
+                                    short* g_d2 = ring16 + r16_off(d, sl16, TWO ? AW_COMP_D2 : AW_COMP_M);
+                                    int lo_c[5], hi_c[5];
+#pragma unroll
+                                    for (int c = 0; c < 5; ++c) lo_c[c] = hi_c[c] = INT_MIN;
+                                    int akM = INT_MIN, akAll = INT_MIN, endval = INT_MIN;
+                                    bool oob = false;
+                                    const unsigned utl = (unsigned)tlen, upl = (unsigned)plen;
+                                    // only diagonals the row can occupy at this step: [mn - t, mxk + t], inside the trapezoid
+                                    const int i_lo = max(t, mn - t - base_k), i_hi = min(BAND_WP - 1 - t, mxk + t - base_k);
+                                    // cells just outside the clipped range still hold an older row: later steps of this
+                                    // band read up to (BAND_T - t) + 1 columns beyond it, so NULL that margin
+                                    {
+                                        const int mg = BAND_T - t + 1;
+                                        if (tid < 2 * mg) {
+                                            const int i = (tid < mg) ? (i_lo - 1 - tid) : (i_hi + 1 + (tid - mg));
+                                            if (i >= 0 && i < BAND_WP) {
+                                                w_m[i] = NULL16;
+                                                w_i1[i] = NULL16;
+                                                w_d1[i] = NULL16;
+                                                if (TWO) {
+                                                    w_i2[i] = NULL16;
+                                                    w_d2[i] = NULL16;
+                                                }
+                                            }
+                                        }
+                                    }
+                                    constexpr int J = 4;  // cells per thread advanced in lockstep (independent chains)
+                                    for (int i0 = i_lo + tid; i0 <= i_hi; i0 += J * NT) {
+                                        int ii[J], kk[J], vm[J], vpre[J], vi1[J], vd1[J], vi2[J], vd2[J], ext[J];
+                                        bool act[J], more[J];
+#pragma unroll
+                                        for (int j = 0; j < J; ++j) {
+                                            act[j] = (i0 + j * NT) <= i_hi;
+                                            ii[j] = act[j] ? i0 + j * NT : i_lo;
+                                            kk[j] = base_k + ii[j];
+                                        }
+#pragma unroll
+                                        for (int j = 0; j < J; ++j) {
+                                            const int i = ii[j];
+                                            int i1 = max((int)r_mo1[i - 1], (int)r_i1[i - 1]) + 1;
+                                            const int d1 = max((int)r_mo1[i + 1], (int)r_d1[i + 1]);
+                                            int i2 = NULL16, d2 = NULL16, ins = i1, del = d1;
+                                            if (TWO) {
+                                                i2 = max((int)r_mo2[i - 1], (int)r_i2[i - 1]) + 1;
+                                                d2 = max((int)r_mo2[i + 1], (int)r_d2[i + 1]);
+                                                ins = max(i1, i2);
+                                                del = max(d1, d2);
+                                            }
+                                            int m = max(del, max((int)r_mx[i] + 1, ins));
+                                            vpre[j] = m;
+                                            if ((unsigned)m > utl || (unsigned)(m - kk[j]) > upl) m = NULL16;
+                                            vm[j] = m;
+                                            vi1[j] = (i1 < 0) ? (int)NULL16 : i1;  // all negative offsets are equivalent: stop the +1 drift
+                                            vd1[j] = d1;
+                                            vi2[j] = (i2 < 0) ? (int)NULL16 : i2;
+                                            vd2[j] = d2;
+                                        }
+#pragma unroll
+                                        for (int j = 0; j < J; ++j) {  // first extend round, branch-free
+                                            const bool valid = vm[j] >= 0;
+                                            extend_first<BITS>(sv, valid ? kk[j] : 0, valid ? vm[j] : 0, ext[j], more[j]);
+                                            more[j] = more[j] && valid;
+                                            if (valid) vm[j] += ext[j];
+                                        }
+#pragma unroll
+                                        for (int j = 0; j < J; ++j)  // long match runs (rare)
+                                            if (more[j]) vm[j] = extend_rest<BITS>(sv, kk[j], vm[j]);
+#pragma unroll
+                                        for (int j = 0; j < J; ++j) {
+                                            if (!act[j]) continue;
+                                            const int i = ii[j], k = kk[j], m = vm[j], i1 = vi1[j], d1 = vd1[j], i2 = vi2[j], d2 = vd2[j];
+                                            w_m[i] = (short)m;
+                                            w_i1[i] = (short)i1;
+                                            w_d1[i] = (short)d1;
+                                            if (TWO) {
+                                                w_i2[i] = (short)i2;
+                                                w_d2[i] = (short)d2;
+                                            }
+                                            if (k >= ka && k <= kb) {  // cells this tile owns
+                                                if (k >= kmin_alloc && k <= kmax_alloc) {
+                                                    g_m[k] = (short)m;
+                                                    g_i1[k] = (short)i1;
+                                                    g_d1[k] = (short)d1;
+                                                    if (TWO) {
+                                                        g_i2[k] = (short)i2;
+                                                        g_d2[k] = (short)d2;
+                                                    }
+                                                } else if (m >= 0 || i1 >= 0 || d1 >= 0 || i2 >= 0 || d2 >= 0) {
+                                                    oob = true;  // valid data outside the allocated diagonals
+                                                }
+                                                if (vpre[j] >= 0) akAll = max(akAll, 2 * vpre[j] - k);
+                                                if (m >= 0) {
+                                                    if (lo_c[0] == INT_MIN) lo_c[0] = -k;
+                                                    hi_c[0] = k;
+                                                    akM = max(akM, 2 * m - k);
+                                                }
+                                                auto track = [&](int c, int v) {
+                                                    if (v >= 0) {
+                                                        if ((unsigned)v > utl || (unsigned)(v - k) > upl) oob = true;
+                                                        if (lo_c[c] == INT_MIN) lo_c[c] = -k;
+                                                        hi_c[c] = k;
+                                                    }
+                                                };
+                                                track(AW_COMP_I1, i1);
+                                                track(AW_COMP_D1, d1);
+                                                if (TWO) {
+                                                    track(AW_COMP_I2, i2);
+                                                    track(AW_COMP_D2, d2);
+                                                }
+                                                if (k == k_end) endval = (ce == AW_COMP_M) ? m : (ce == AW_COMP_I1) ? i1 : (ce == AW_COMP_D1) ? d1 : (ce == AW_COMP_I2) ? i2 : d2;
+                                            }
+                                        }
+                                    }
+                                    int* tab = band_tab + (d * (BAND_T + 1) + t) * BAND_TAB;
+#pragma unroll
+                                    for (int c = 0; c < 5; ++c) {
+                                        if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
+                                        red_max<256>(tab, RED_HI + c, hi_c[c]);
+                                        red_max<256>(tab, RED_LO + c, lo_c[c]);
+                                    }
+                                    red_max<256>(tab, RED_AKM, akM);
+                                    red_max<256>(tab, RED_AKALL, akAll);
+                                    red_max<256>(tab, RED_END, endval);
+                                    if (__any_sync(0xffffffffu, oob) && (tid & 31) == 0) s_band_flag = 1;
+                                    cta_sync<NT>();
+                                }
+                                w_cells += (unsigned long long)BAND_T * (unsigned long long)(kb - ka + 1) * NCOMP;
+                            }
+                            w_steps += BAND_T;
+                        }
+                        cta_sync<NT>();
+                        if (band_fail || s_band_flag) {
+                            band_fail = true;
+                            break;
+                        }
+                        // ---- replay WFA2's alternation over the band's steps; publish the rows' metadata ----
+                        int sl = slotS;
+                        for (int t = 1; t <= BAND_T && !band_break && !fb_end; ++t) {
+                            sl = (sl + 1 == rn16) ? 0 : sl + 1;
+                            bool done_d[2];
+                            int ak_d[2];
+                            for (int d = 0; d < 2; ++d) {
+                                const int* tab = band_tab + (d * (BAND_T + 1) + t) * BAND_TAB;
+                                Meta16& q = meta16[d * rn16 + sl];
+#pragma unroll
+                                for (int c = 0; c < 5; ++c) {
+                                    const int h = tab[RED_HI + c], l = tab[RED_LO + c];
+                                    q.lo[c] = (h == INT_MIN) ? 1 : -l;
+                                    q.hi[c] = (h == INT_MIN) ? 0 : h;
+                                }
+                                q.akM = tab[RED_AKM];
+                                q.akAll = tab[RED_AKALL];
+                                done_d[d] = tab[RED_END] >= tlen;
+                                ak_d[d] = q.akM;
+                            }
+                            // forward step S+t
+                            score_f = S + t;
+                            f_ak = max(f_ak, max(0, done_d[0] ? 0 : ak_d[0]));
+                            last_forward = true;
+                            if (AW_BIALIGN_PHASE1_END_REACHED_RETURNS && done_d[0]) {
+                                fb_end = true;
+                                break;
+                            }
+                            if (f_ak + r_ak >= max_antidiagonal) {
+                                band_break = true;  // reverse stays at S+t-1
+                                break;
+                            }
+                            // reverse step S+t
+                            score_r = S + t;
+                            r_ak = max(r_ak, max(0, done_d[1] ? 0 : ak_d[1]));
+                            last_forward = false;
+                            if (AW_BIALIGN_PHASE1_END_REACHED_RETURNS && done_d[1]) {
+                                fb_end = true;
+                                break;
+                            }
+                            if (f_ak + r_ak >= max_antidiagonal) band_break = true;
+                        }
+                        if (!band_break && !fb_end) {
+                            S += BAND_T;
+                            slotS += BAND_T;
+                            if (slotS >= rn16) slotS -= rn16;
+                        }
+                        cta_sync<NT>();
+                    }
+                    if (band_fail) {
+                        cyc[5] += 1;
+                        // redo phase 1 on the generic path from score 0 (rows 0 are still in the int32 ring)
+                        score_f = score_r = 0;
+                        f_ak = max(0, ring_meta[0 * ring_n + 0].akM);
+                        r_ak = max(0, ring_meta[1 * ring_n + 0].akM);
+                        last_forward = false;
+                        cur_slot[0] = cur_slot[1] = 0;
+                    } else {
+                        band_done = true;
+                        if (!fb_end) {
+                            // ---- hand-over: last `scope` rows of each direction -> generic int32 ring ----
+                            for (int d = 0; d < 2; ++d) {
+                                const int sd = (d == 0) ? score_f : score_r;
+                                int sl_top = slotS + (sd - S);
+                                if (sl_top >= rn16) sl_top -= rn16;
+                                for (int j = 0; j < scope && sd - j >= 0; ++j) {
+                                    int sl16 = sl_top - j;
+                                    if (sl16 < 0) sl16 += rn16;
+                                    const int sl32 = (sd - j) % ring_n;
+                                    const Meta16& q = meta16[d * rn16 + sl16];
+                                    SlotMeta& mt = ring_meta[d * ring_n + sl32];
+#pragma unroll
+                                    for (int c = 0; c < 5; ++c) {
+                                        mt.lo[c] = q.lo[c];
+                                        mt.hi[c] = q.hi[c];
+                                        if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
+                                        const short* src = ring16 + r16_off(d, sl16, c);
+                                        WS* dst = ws + ring_off(d, sl32, c);
+                                        for (int k = q.lo[c] + tid; k <= q.hi[c]; k += NT) {
+                                            const int v = src[k];
+                                            dst[k] = to_ws<WS>(v < 0 ? AW_NULLV : v);
+                                        }
+                                    }
+                                    mt.akM = q.akM;
+                                    mt.akAll = q.akAll;
+                                }
+                                cur_slot[d] = sd % ring_n;
+                            }
+                            cta_sync<NT>();
+                        }
+                    }
+                }
                 // ---- phase 1: forward step s_f+1 and (speculative) reverse step s_r+1 share one barrier ----
-                while (!fb_end && status == ST_OK) {
+                while (!band_done && !fb_end && status == ST_OK) {
                     if (f_ak + r_ak >= max_antidiagonal) break;
                     const int slot_f = next_slot(cur_slot[0]), slot_r = next_slot(cur_slot[1]);
                     const Range rf = launch_dir(0, score_f + 1, slot_f);
@@ -996,7 +1413,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
                     if (tid == 0) {
                         int m = 0;
                         if (sp.cb == AW_COMP_M) m = extend_cell<BITS>(sv, 0, 0);
-                        ws[hist_off(0, 1, 0, sp.cb)] = m;
+                        ws[hist_off(0, 1, 0, sp.cb)] = to_ws<WS>(m);
                         if (sp.cb == AW_COMP_M && sp.ce == AW_COMP_M && k_end == 0) r[RED_END] = m;
                     }
                     cta_sync<NT>();
@@ -1071,10 +1488,10 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
                     int out[5];
 #pragma unroll
                     for (int c = 0; c < 5; ++c) out[c] = hist_off(off, width, lo, (TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M);
-                    wf_cells<NT, BITS, TWO>(ws, in, out, lo, hi, sv, k_end, sp.ce, red[0][red_i]);
+                    wf_cells<NT, BITS, TWO, WS>(ws, in, out, lo, hi, sv, k_end, sp.ce, red[0][red_i]);
                     cta_sync<NT>();
                     wf_finish<TWO>(red[0][red_i], lo, hi, so);
-                    if (so.ambiguous) wf_rescan<NT, TWO>(ws, out, lo, hi, plen, tlen, red[0][red_i], so);
+                    if (so.ambiguous) wf_rescan<NT, TWO, WS>(ws, out, lo, hi, plen, tlen, red[0][red_i], so);
                     w_cells += (unsigned long long)width * NCOMP;
                     store_meta(mt, so);
                     mt.clo = lo;
