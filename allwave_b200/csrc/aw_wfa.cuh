@@ -856,16 +856,26 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
                         const WS* p0 = ws + ring_off(d0, slot0, c);
                         const WS* p1 = ws + ring_off(d1, sl1, c);
                         int best = INT_MAX;
-                        for (int k0 = max_lo + tid; k0 <= min_hi; k0 += NT) {
-                            const int k1 = kinv - k0;
-                            const int h0 = p0[k0], h1 = p1[k1];
-                            if (h0 + h1 >= tlen) {
-                                if (c != AW_COMP_M) {  // indel2indel: the forward cell must be in bounds
-                                    const int kk = (d0 == 0) ? k0 : k1, hh = (d0 == 0) ? h0 : h1;
-                                    if (hh - kk > plen || hh > tlen) continue;
+                        // 4 diagonals per thread per round: the 8 loads are independent and issue together
+                        for (int kb0 = max_lo + tid; kb0 <= min_hi && best == INT_MAX; kb0 += 4 * NT) {
+                            int h0[4], h1[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int k0 = min(kb0 + j * NT, min_hi);  // clamped duplicates are re-tested harmlessly
+                                h0[j] = p0[k0];
+                                h1[j] = p1[kinv - k0];
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int k0 = kb0 + j * NT;
+                                if (k0 > min_hi || best != INT_MAX) continue;
+                                if (h0[j] + h1[j] >= tlen) {
+                                    if (c != AW_COMP_M) {  // indel2indel: the forward cell must be in bounds
+                                        const int kk = (d0 == 0) ? k0 : kinv - k0, hh = (d0 == 0) ? h0[j] : h1[j];
+                                        if (hh - kk > plen || hh > tlen) continue;
+                                    }
+                                    best = k0;
                                 }
-                                best = k0;
-                                break;
                             }
                         }
                         best = __reduce_min_sync(0xffffffffu, best);

@@ -1,0 +1,495 @@
+// allwave.hpp -- C++17 host-side mirror of allwave's library surface for the alignment path,
+// sitting above the C ABI of liballwave_cuda.so (include/allwave_cuda.h).
+//
+// The reference's host code is Rust; no Rust toolchain exists in this image, so the host side is
+// written in C++ with the same names, argument meaning and error behaviour:
+//   Sequence, AlignmentParams, AlignmentMode, AlignmentResult, SparsificationStrategy   src/types.rs
+//   parse_scores, alignment_to_paf, process_alignments_with_callback                    src/lib.rs:57-153
+//   AllPairIterator {with_options, pair_count, get_pairs, for_each_with_callback, next} src/iterator.rs:25-252
+//   apply_random_sparsification, compute_connectivity_probability                       src/iterator.rs:256-334
+//   extract_tree_pairs, build_knn_graph, generate_random_pairs                          src/knn_graph.rs:12-174
+//   mash distance from Jaccard                                                          src/mash.rs:59-74
+//   the -p grammar of the CLI                                                           src/main.rs:136-203
+// Everything numeric on the alignment path (sketches, Jaccard counts, orientation, wavefronts,
+// CIGAR, PAF text) is computed on the GPU through the C ABI; this header only builds pair lists,
+// partitions them and forwards results.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/allwave_cuda.h"
+
+namespace allwave {
+
+struct Sequence {
+    std::string id;
+    std::vector<uint8_t> seq;
+};
+
+struct AlignmentParams {
+    int32_t match_score = 0;
+    int32_t mismatch_penalty = 5;
+    int32_t gap_open = 8;
+    int32_t gap_extend = 2;
+    std::optional<int32_t> gap2_open = 24;
+    std::optional<int32_t> gap2_extend = 1;
+    std::optional<double> max_divergence;
+    static AlignmentParams edit_distance() {
+        AlignmentParams p;
+        p.mismatch_penalty = p.gap_open = p.gap_extend = 1;
+        p.gap2_open.reset();
+        p.gap2_extend.reset();
+        return p;
+    }
+    bool operator==(const AlignmentParams& o) const {
+        return match_score == o.match_score && mismatch_penalty == o.mismatch_penalty && gap_open == o.gap_open && gap_extend == o.gap_extend &&
+               gap2_open == o.gap2_open && gap2_extend == o.gap2_extend && max_divergence == o.max_divergence;
+    }
+    aw_params to_c() const {
+        aw_params p;
+        std::memset(&p, 0, sizeof(p));
+        p.match_score = match_score;
+        p.mismatch_penalty = mismatch_penalty;
+        p.gap_open = gap_open;
+        p.gap_extend = gap_extend;
+        if (gap2_open) { p.gap2_open = *gap2_open; p.has_gap2_open = 1; }
+        if (gap2_extend) { p.gap2_extend = *gap2_extend; p.has_gap2_extend = 1; }
+        return p;
+    }
+};
+
+enum class AlignmentMode { EditDistance, SinglePieceAffine, TwoPieceAffine };
+inline AlignmentMode alignment_mode_from_params(const AlignmentParams& p) {
+    if (p.gap2_open && p.gap2_extend) return AlignmentMode::TwoPieceAffine;
+    if (p.gap_open == p.gap_extend && p.gap_open == p.mismatch_penalty) return AlignmentMode::EditDistance;
+    return AlignmentMode::SinglePieceAffine;
+}
+
+struct AlignmentResult {
+    size_t query_idx = 0, target_idx = 0;
+    size_t query_start = 0, query_end = 0, target_start = 0, target_end = 0;
+    bool is_reverse = false;
+    std::vector<uint8_t> cigar_bytes;  // WFA2 letters; filled only when requested
+    int32_t score = 0;
+    size_t num_matches = 0, alignment_length = 0;
+    std::string cigar;  // cigar_bytes_to_string(cigar_bytes), produced on the GPU
+    std::string paf;    // alignment_to_paf(result, sequences), produced on the GPU
+};
+
+struct SparsificationStrategy {
+    enum Kind { None, Random, Auto, Connectivity, TreeSampling } kind = None;
+    double value = 0.0;  // Random: keep fraction; Connectivity: giant-component probability
+    size_t k_nearest = 0, k_farthest = 0;
+    double random_fraction = 0.0;
+    std::optional<size_t> kmer_size;
+    static SparsificationStrategy none() { return {}; }
+    static SparsificationStrategy random(double f) { SparsificationStrategy s; s.kind = Random; s.value = f; return s; }
+    static SparsificationStrategy automatic() { SparsificationStrategy s; s.kind = Auto; return s; }
+    static SparsificationStrategy connectivity(double p) { SparsificationStrategy s; s.kind = Connectivity; s.value = p; return s; }
+    static SparsificationStrategy tree(size_t kn, size_t kf, double rf, std::optional<size_t> k = std::nullopt) {
+        SparsificationStrategy s; s.kind = TreeSampling; s.k_nearest = kn; s.k_farthest = kf; s.random_fraction = rf; s.kmer_size = k; return s;
+    }
+};
+
+// ---- parse_scores (src/lib.rs:116-153) ----
+inline AlignmentParams parse_scores(const std::string& scores_str) {
+    std::vector<int32_t> v;
+    size_t b = 0;
+    for (;;) {
+        size_t e = scores_str.find(',', b);
+        std::string tok = scores_str.substr(b, e == std::string::npos ? std::string::npos : e - b);
+        size_t l = tok.find_first_not_of(" \t\n\r\f\v"), r = tok.find_last_not_of(" \t\n\r\f\v");
+        tok = l == std::string::npos ? "" : tok.substr(l, r - l + 1);
+        size_t i = 0;
+        bool neg = false;
+        if (i < tok.size() && (tok[i] == '+' || tok[i] == '-')) neg = tok[i++] == '-';
+        if (i >= tok.size()) throw std::invalid_argument("Failed to parse scores: invalid digit found in string");
+        int64_t x = 0;
+        for (; i < tok.size(); ++i) {
+            if (tok[i] < '0' || tok[i] > '9') throw std::invalid_argument("Failed to parse scores: invalid digit found in string");
+            x = x * 10 + (tok[i] - '0');
+            if (x > (int64_t)INT32_MAX + 1) throw std::invalid_argument("Failed to parse scores: number too large to fit in target type");
+        }
+        if (neg) x = -x;
+        if (x > INT32_MAX || x < INT32_MIN) throw std::invalid_argument("Failed to parse scores: number too large to fit in target type");
+        v.push_back((int32_t)x);
+        if (e == std::string::npos) break;
+        b = e + 1;
+    }
+    if (v.size() != 4 && v.size() != 6)
+        throw std::invalid_argument("Invalid number of scores: " + std::to_string(v.size()) + ". Expected 4 or 6 values.");
+    AlignmentParams p;
+    p.match_score = v[0];
+    p.mismatch_penalty = v[1];
+    p.gap_open = v[2];
+    p.gap_extend = v[3];
+    if (v.size() == 6) {
+        p.gap2_open = v[4];
+        p.gap2_extend = v[5];
+    } else {
+        p.gap2_open.reset();
+        p.gap2_extend.reset();
+    }
+    return p;
+}
+
+// ---- the -p grammar (src/main.rs:136-203) ----
+inline SparsificationStrategy parse_sparsification(const std::string& s) {
+    auto parse_f = [](const std::string& t, const char* msg) -> double {
+        try {
+            size_t pos = 0;
+            double v = std::stod(t, &pos);
+            if (pos != t.size()) throw std::invalid_argument(msg);
+            return v;
+        } catch (const std::exception&) { throw std::invalid_argument(msg); }
+    };
+    auto parse_u = [](const std::string& t, const char* msg) -> size_t {
+        if (t.empty()) throw std::invalid_argument(msg);
+        size_t v = 0;
+        size_t i = (t[0] == '+') ? 1 : 0;
+        if (i >= t.size()) throw std::invalid_argument(msg);
+        for (; i < t.size(); ++i) {
+            if (t[i] < '0' || t[i] > '9') throw std::invalid_argument(msg);
+            v = v * 10 + (size_t)(t[i] - '0');
+        }
+        return v;
+    };
+    if (s == "none") return SparsificationStrategy::none();
+    if (s == "auto") return SparsificationStrategy::automatic();
+    if (s.rfind("random:", 0) == 0) {
+        double f = parse_f(s.substr(7), "Invalid random fraction");
+        if (f <= 0.0 || f > 1.0) throw std::invalid_argument("Random fraction must be between 0 and 1");
+        return SparsificationStrategy::random(f);
+    }
+    if (s.rfind("giant:", 0) == 0 || s.rfind("connectivity:", 0) == 0) {
+        const bool giant = s[0] == 'g';
+        double p = parse_f(s.substr(giant ? 6 : 13), giant ? "Invalid giant component probability" : "Invalid connectivity probability");
+        if (p <= 0.0 || p >= 1.0)
+            throw std::invalid_argument(giant ? "Giant component probability must be between 0 and 1" : "Connectivity probability must be between 0 and 1");
+        return SparsificationStrategy::connectivity(p);
+    }
+    if (s.rfind("tree:", 0) == 0) {
+        std::vector<std::string> parts;
+        std::string rest = s.substr(5);
+        size_t b = 0;
+        for (;;) {
+            size_t e = rest.find(':', b);
+            parts.push_back(rest.substr(b, e == std::string::npos ? std::string::npos : e - b));
+            if (e == std::string::npos) break;
+            b = e + 1;
+        }
+        if (parts.size() < 3 || parts.size() > 4)
+            throw std::invalid_argument("Invalid tree format. Use: tree:<k_nearest>:<k_farthest>:<random_fraction>[:<kmer_size>]");
+        size_t kn = parse_u(parts[0], "Invalid k nearest count"), kf = parse_u(parts[1], "Invalid k farthest count");
+        double rf = parse_f(parts[2], "Invalid random fraction");
+        if (kn == 0 && kf == 0) throw std::invalid_argument("At least one of k_nearest or k_farthest must be greater than 0");
+        if (!(rf >= 0.0 && rf <= 1.0)) throw std::invalid_argument("Random fraction must be between 0 and 1");
+        std::optional<size_t> k;
+        if (parts.size() == 4) {
+            size_t kk = parse_u(parts[3], "Invalid k-mer size");
+            if (kk < 3 || kk > 31) throw std::invalid_argument("K-mer size must be between 3 and 31");
+            k = kk;
+        }
+        return SparsificationStrategy::tree(kn, kf, rf, k);
+    }
+    throw std::invalid_argument("Invalid sparsification strategy. Use: none, auto, giant:<probability>, random:<fraction>, or tree:<near>:<far>:<random>[:<kmer>]");
+}
+
+// ---- Rust DefaultHasher over a str: SipHash-1-3, zero keys, bytes || 0xFF ----
+inline uint64_t default_hash_str(const std::string& s) {
+    auto rotl = [](uint64_t x, int b) { return (x << b) | (x >> (64 - b)); };
+    uint64_t v0 = 0x736f6d6570736575ULL, v1 = 0x646f72616e646f6dULL, v2 = 0x6c7967656e657261ULL, v3 = 0x7465646279746573ULL;
+    auto round = [&]() {
+        v0 += v1; v1 = rotl(v1, 13); v1 ^= v0; v0 = rotl(v0, 32);
+        v2 += v3; v3 = rotl(v3, 16); v3 ^= v2;
+        v0 += v3; v3 = rotl(v3, 21); v3 ^= v0;
+        v2 += v1; v1 = rotl(v1, 17); v1 ^= v2; v2 = rotl(v2, 32);
+    };
+    std::string m = s;
+    m.push_back((char)0xFF);
+    size_t i = 0, len = m.size();
+    for (; i + 8 <= len; i += 8) {
+        uint64_t w = 0;
+        for (int j = 0; j < 8; ++j) w |= (uint64_t)(uint8_t)m[i + j] << (8 * j);
+        v3 ^= w; round(); v0 ^= w;
+    }
+    uint64_t b = (uint64_t)(len & 0xff) << 56;
+    for (int j = 0; i + j < len; ++j) b |= (uint64_t)(uint8_t)m[i + j] << (8 * j);
+    v3 ^= b; round(); v0 ^= b;
+    v2 ^= 0xff;
+    round(); round(); round();
+    return v0 ^ v1 ^ v2 ^ v3;
+}
+
+// hash("idA:idB") as f64 / u64::MAX as f64 < fraction (src/iterator.rs:262-280, src/knn_graph.rs:161-174)
+inline bool keep_pair(const std::string& a, const std::string& b, double fraction) {
+    const uint64_t h = default_hash_str(a + ":" + b);
+    return (double)h / 18446744073709551616.0 < fraction;
+}
+
+// src/iterator.rs:300-334
+inline double compute_connectivity_probability(size_t n, double connectivity_prob) {
+    if (n <= 1) return 1.0;
+    const double x = std::min(0.999, std::max(0.001, connectivity_prob));
+    if (n <= 10) {
+        switch (n) {
+            case 2: return 1.0;
+            case 3: return 0.8;
+            case 4: return 0.7;
+            case 5: return 0.6;
+            default: return 0.5;
+        }
+    }
+    const double n_f = (double)n, log_n = std::log(n_f), c = -std::log(-std::log(x));
+    return std::min(1.0, std::max(0.001, (log_n + c) / n_f));
+}
+
+// src/mash.rs:59-74 from the GPU's Jaccard counts
+inline double mash_distance_from_counts(uint32_t inter, uint32_t uni, int k) {
+    const double j = uni == 0 ? 0.0 : (double)inter / (double)uni;
+    if (j <= 0.0) return 1.0;
+    const double ratio = (2.0 * j) / (1.0 + j);
+    if (ratio <= 0.0) return 1.0;
+    return (-1.0 / (double)k) * std::log(ratio);
+}
+
+// src/knn_graph.rs:112-143 (stable sort: ties keep ascending neighbour index)
+inline std::vector<std::pair<size_t, size_t>> build_knn_graph(const std::vector<std::vector<double>>& dm, size_t k_neighbors, bool farthest) {
+    const size_t n = dm.size();
+    std::vector<std::pair<size_t, size_t>> pairs;
+    for (size_t i = 0; i < n; ++i) {
+        std::vector<std::pair<double, size_t>> nb;
+        for (size_t j = 0; j < n; ++j)
+            if (i != j) nb.emplace_back(dm[i][j], j);
+        if (farthest) std::stable_sort(nb.begin(), nb.end(), [](auto& a, auto& b) { return a.first > b.first; });
+        else std::stable_sort(nb.begin(), nb.end(), [](auto& a, auto& b) { return a.first < b.first; });
+        for (size_t q = 0; q < std::min(k_neighbors, nb.size()); ++q) pairs.emplace_back(i, nb[q].second);
+    }
+    return pairs;
+}
+
+// RAII handle of one aw_ctx (one GPU)
+class Context {
+   public:
+    explicit Context(int device = 0) {
+        int rc = aw_create(device, &ctx_);
+        if (rc != AW_OK) throw std::runtime_error(std::string("aw_create: ") + aw_strerror(rc) + ": " + aw_last_error());
+    }
+    // non-owning view of a context created elsewhere (e.g. by a foreign-language binding)
+    Context(aw_ctx* borrowed, bool own) : ctx_(borrowed), own_(own) {}
+    ~Context() {
+        if (own_) aw_destroy(ctx_);
+    }
+    Context(const Context&) = delete;
+    Context& operator=(const Context&) = delete;
+    aw_ctx* get() const { return ctx_; }
+    void load(const std::vector<Sequence>& seqs) {
+        std::vector<const uint8_t*> p(seqs.size());
+        std::vector<uint64_t> l(seqs.size());
+        std::vector<const char*> ids(seqs.size());
+        for (size_t i = 0; i < seqs.size(); ++i) {
+            p[i] = seqs[i].seq.data();
+            l[i] = seqs[i].seq.size();
+            ids[i] = seqs[i].id.c_str();
+        }
+        int rc = aw_load_sequences(ctx_, (uint32_t)seqs.size(), p.data(), l.data(), ids.data());
+        if (rc != AW_OK) throw std::runtime_error(std::string("aw_load_sequences: ") + aw_strerror(rc) + ": " + aw_last_error());
+    }
+
+   private:
+    aw_ctx* ctx_ = nullptr;
+    bool own_ = true;
+};
+
+// src/knn_graph.rs:12-52; the sketches and the n^2 Jaccard counts come from the GPU (sequences must be loaded)
+inline std::vector<std::pair<size_t, size_t>> extract_tree_pairs(Context& ctx, const std::vector<Sequence>& seqs, size_t k_nearest, size_t k_farthest,
+                                                                 double random_fraction, size_t kmer_size) {
+    const size_t n = seqs.size();
+    std::vector<std::pair<size_t, size_t>> all;
+    if (n < 2) return all;
+    std::vector<uint32_t> inter(n * n), uni(n * n);
+    int rc = aw_mash_jaccard_counts(ctx.get(), (int)kmer_size, 1000, inter.data(), uni.data());
+    if (rc != AW_OK) throw std::runtime_error(std::string("aw_mash_jaccard_counts: ") + aw_strerror(rc) + ": " + aw_last_error());
+    std::vector<std::vector<double>> dm(n, std::vector<double>(n, 0.0));
+    for (size_t i = 0; i < n; ++i)
+        for (size_t j = i + 1; j < n; ++j) dm[i][j] = dm[j][i] = mash_distance_from_counts(inter[i * n + j], uni[i * n + j], (int)kmer_size);
+    if (k_nearest > 0) {
+        auto p = build_knn_graph(dm, k_nearest, false);
+        all.insert(all.end(), p.begin(), p.end());
+    }
+    if (k_farthest > 0) {
+        auto p = build_knn_graph(dm, k_farthest, true);
+        all.insert(all.end(), p.begin(), p.end());
+    }
+    if (random_fraction > 0.0)
+        for (size_t i = 0; i < n; ++i)
+            for (size_t j = 0; j < n; ++j)
+                if (i != j && keep_pair(seqs[i].id, seqs[j].id, random_fraction)) all.emplace_back(i, j);
+    std::sort(all.begin(), all.end());
+    all.erase(std::unique(all.begin(), all.end()), all.end());
+    return all;
+}
+
+// the ordered pair list of AllPairIterator::with_options (src/iterator.rs:37-77)
+inline std::vector<std::pair<size_t, size_t>> build_pair_list(Context& ctx, const std::vector<Sequence>& sequences, bool exclude_self,
+                                                              const SparsificationStrategy& sp) {
+    const size_t n = sequences.size();
+    if (sp.kind == SparsificationStrategy::TreeSampling)
+        return extract_tree_pairs(ctx, sequences, sp.k_nearest, sp.k_farthest, sp.random_fraction, sp.kmer_size.value_or(15));
+    double keep = 1.0;
+    bool filter = true;
+    if (sp.kind == SparsificationStrategy::None) filter = false;
+    else if (sp.kind == SparsificationStrategy::Random) keep = sp.value;
+    else if (sp.kind == SparsificationStrategy::Auto) keep = compute_connectivity_probability(n, 0.95);
+    else keep = compute_connectivity_probability(n, sp.value);
+    std::vector<std::pair<size_t, size_t>> pairs;
+    for (size_t i = 0; i < n; ++i)
+        for (size_t j = 0; j < n; ++j) {
+            if (exclude_self && i == j) continue;
+            if (filter && !keep_pair(sequences[i].id, sequences[j].id, keep)) continue;
+            pairs.emplace_back(i, j);
+        }
+    return pairs;
+}
+
+using Callback = std::function<void(const AlignmentResult&)>;  // throw to abort the run (mirrors a callback Err)
+
+class AllPairIterator {
+   public:
+    // AllPairIterator::new (src/iterator.rs:25-28) == with_options(seqs, params, true, false, None)
+    // with_options (src/iterator.rs:30-92); the sequences must already be loaded into ctx
+    // (optimize("O0"): g++ 13.3 segfaults in its GIMPLE ccp pass on this constructor at -O1 and above)
+    __attribute__((optimize("O0"))) AllPairIterator(Context& ctx, const std::vector<Sequence>& sequences, const AlignmentParams& params,
+                                                   bool exclude_self = true, bool use_mash_orientation = false,
+                                                   const SparsificationStrategy& sp = SparsificationStrategy())
+        : ctx_(ctx), seqs_(sequences), params_(params), orientation_params_(AlignmentParams::edit_distance()), exclude_self_(exclude_self),
+          use_mash_(use_mash_orientation), pairs_(build_pair_list(ctx, sequences, exclude_self, sp)) {}
+    AllPairIterator& with_orientation_params(AlignmentParams p) {
+        orientation_params_ = std::move(p);
+        return *this;
+    }
+    size_t pair_count() const { return pairs_.size(); }
+    const std::vector<std::pair<size_t, size_t>>& get_pairs() const { return pairs_; }
+
+    // for_each_with_callback (src/iterator.rs:127-137,208-252): the whole remaining pair list goes to the GPU
+    void for_each_with_callback(const Callback& cb, uint32_t flags = 0) {
+        run(next_, pairs_.size() - next_, cb, flags);
+        next_ = pairs_.size();
+    }
+    // impl Iterator::next (src/iterator.rs:151-171): strictly in pair order; batches are prefetched
+    std::optional<AlignmentResult> next() {
+        if (buf_pos_ == buffered_.size()) {
+            buffered_.clear();
+            buf_pos_ = 0;
+            if (next_ >= pairs_.size()) return std::nullopt;
+            const size_t cnt = std::min<size_t>(prefetch_, pairs_.size() - next_);
+            run(next_, cnt, [&](const AlignmentResult& r) { buffered_.push_back(r); }, 0);
+            next_ += cnt;
+        }
+        return buffered_[buf_pos_++];
+    }
+    void set_prefetch(size_t n) { prefetch_ = n ? n : 1; }
+
+   private:
+    struct Trampoline {
+        const Callback* cb;
+        std::exception_ptr err;
+        uint32_t flags;
+    };
+    static int c_callback(const aw_result* r, void* user) {
+        Trampoline* t = static_cast<Trampoline*>(user);
+        AlignmentResult a;
+        a.query_idx = r->query_idx;
+        a.target_idx = r->target_idx;
+        a.query_start = r->query_start;
+        a.query_end = r->query_end;
+        a.target_start = r->target_start;
+        a.target_end = r->target_end;
+        a.is_reverse = r->is_reverse != 0;
+        a.score = r->score;
+        a.num_matches = r->num_matches;
+        a.alignment_length = r->alignment_length;
+        if (r->cigar_bytes) a.cigar_bytes.assign(r->cigar_bytes, r->cigar_bytes + r->cigar_len);
+        if (r->cg) a.cigar.assign(r->cg, r->cg_len);
+        if (r->paf) a.paf.assign(r->paf, r->paf_len);
+        try {
+            (*t->cb)(a);
+        } catch (...) {
+            t->err = std::current_exception();
+            return 1;
+        }
+        return 0;
+    }
+    void run(size_t first, size_t count, const Callback& cb, uint32_t flags) {
+        if (count == 0) return;
+        std::vector<aw_pair> cp(count);
+        for (size_t i = 0; i < count; ++i) {
+            cp[i].query_idx = (uint32_t)pairs_[first + i].first;
+            cp[i].target_idx = (uint32_t)pairs_[first + i].second;
+        }
+        const aw_params p = params_.to_c();
+        Trampoline t{&cb, nullptr, flags};
+        int rc = aw_align_pairs(ctx_.get(), &p, use_mash_ ? AW_ORIENT_MASH : AW_ORIENT_WFA, cp.data(), count, flags, &c_callback, &t);
+        if (t.err) std::rethrow_exception(t.err);
+        if (rc != AW_OK) throw std::runtime_error(std::string("aw_align_pairs: ") + aw_strerror(rc) + ": " + aw_last_error());
+    }
+    Context& ctx_;
+    const std::vector<Sequence>& seqs_;
+    AlignmentParams params_, orientation_params_;
+    bool exclude_self_, use_mash_;
+    std::vector<std::pair<size_t, size_t>> pairs_;
+    size_t next_ = 0, prefetch_ = 4096, buf_pos_ = 0;
+    std::vector<AlignmentResult> buffered_;
+};
+
+// src/lib.rs:57-68
+inline void process_alignments_with_callback(Context& ctx, const std::vector<Sequence>& sequences, AlignmentParams params, const SparsificationStrategy& sp,
+                                             const Callback& cb) {
+    AllPairIterator it(ctx, sequences, std::move(params), true, true, sp);
+    it.for_each_with_callback(cb);
+}
+
+// src/lib.rs:71-112: the PAF line is produced on the GPU together with the CIGAR
+inline const std::string& alignment_to_paf(const AlignmentResult& r, const std::vector<Sequence>&) { return r.paf; }
+
+// src/alignment.rs:178-190 (API surface only; the aligner uses the device copy)
+inline std::vector<uint8_t> reverse_complement(const std::vector<uint8_t>& seq) {
+    std::vector<uint8_t> out(seq.size());
+    for (size_t i = 0; i < seq.size(); ++i) {
+        const uint8_t b = seq[seq.size() - 1 - i];
+        out[i] = (b == 'A' || b == 'a') ? 'T' : (b == 'T' || b == 't') ? 'A' : (b == 'C' || b == 'c') ? 'G' : (b == 'G' || b == 'g') ? 'C' : 'N';
+    }
+    return out;
+}
+
+// plain FASTA (src/main.rs:206-234; ids up to the first whitespace).  bgzf input is out of scope
+inline std::vector<Sequence> read_fasta(const std::string& path) {
+    if (path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0)
+        throw std::runtime_error("gzipped FASTA is not supported by this driver; decompress first");
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("cannot open " + path);
+    std::vector<Sequence> seqs;
+    std::string line;
+    while (std::getline(in, line)) {
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        if (line.empty()) continue;
+        if (line[0] == '>') {
+            size_t e = line.find_first_of(" \t", 1);
+            seqs.push_back(Sequence{line.substr(1, e == std::string::npos ? std::string::npos : e - 1), {}});
+        } else if (!seqs.empty()) {
+            seqs.back().seq.insert(seqs.back().seq.end(), line.begin(), line.end());
+        }
+    }
+    return seqs;
+}
+
+}  // namespace allwave

@@ -1,0 +1,102 @@
+// host_capi.cpp -- C exports of the C++ host mirror (allwave.hpp) so that tests written in
+// Python can check pair scheduling and flag parsing against the oracle.
+#include <cstdlib>
+#include <cstring>
+
+#include "allwave.hpp"
+
+using namespace allwave;
+
+static thread_local std::string g_msg;
+
+extern "C" {
+
+const char* awh_last_message(void) { return g_msg.c_str(); }
+
+int awh_parse_scores(const char* s, aw_params* out) {
+    try {
+        *out = parse_scores(s).to_c();
+        return 0;
+    } catch (const std::exception& e) {
+        g_msg = e.what();
+        return -1;
+    }
+}
+
+int awh_parse_sparsification(const char* s, int* kind, double* value, uint64_t* kn, uint64_t* kf, double* rf, int* kmer) {
+    try {
+        SparsificationStrategy sp = parse_sparsification(s);
+        *kind = (int)sp.kind;
+        *value = sp.value;
+        *kn = sp.k_nearest;
+        *kf = sp.k_farthest;
+        *rf = sp.random_fraction;
+        *kmer = sp.kmer_size ? (int)*sp.kmer_size : 0;
+        return 0;
+    } catch (const std::exception& e) {
+        g_msg = e.what();
+        return -1;
+    }
+}
+
+double awh_connectivity_probability(uint64_t n, double p) { return compute_connectivity_probability((size_t)n, p); }
+uint64_t awh_hash_str(const char* s) { return default_hash_str(s); }
+int awh_mode_from_params(const aw_params* p) {
+    AlignmentParams a;
+    a.match_score = p->match_score;
+    a.mismatch_penalty = p->mismatch_penalty;
+    a.gap_open = p->gap_open;
+    a.gap_extend = p->gap_extend;
+    a.gap2_open.reset();
+    a.gap2_extend.reset();
+    if (p->has_gap2_open) a.gap2_open = p->gap2_open;
+    if (p->has_gap2_extend) a.gap2_extend = p->gap2_extend;
+    return (int)alignment_mode_from_params(a);
+}
+
+// AllPairIterator::with_options(...).get_pairs(); ctx (with the sequences loaded) is needed for the tree strategy only
+int awh_pair_list(aw_ctx* ctx, uint64_t n, const char* const* ids, int kind, double value, uint64_t kn, uint64_t kf, double rf, int kmer,
+                  int exclude_self, uint64_t** out_pairs, uint64_t* out_n) {
+    try {
+        std::vector<Sequence> seqs(n);
+        for (uint64_t i = 0; i < n; ++i) seqs[i].id = ids[i];
+        SparsificationStrategy sp;
+        sp.kind = (SparsificationStrategy::Kind)kind;
+        sp.value = value;
+        sp.k_nearest = kn;
+        sp.k_farthest = kf;
+        sp.random_fraction = rf;
+        if (kmer) sp.kmer_size = (size_t)kmer;
+        Context c(ctx, false);
+        AllPairIterator it(c, seqs, AlignmentParams(), exclude_self != 0, true, sp);
+        const auto& p = it.get_pairs();
+        uint64_t* o = (uint64_t*)std::malloc(sizeof(uint64_t) * 2 * (p.size() ? p.size() : 1));
+        for (size_t i = 0; i < p.size(); ++i) {
+            o[2 * i] = p[i].first;
+            o[2 * i + 1] = p[i].second;
+        }
+        *out_pairs = o;
+        *out_n = p.size();
+        return 0;
+    } catch (const std::exception& e) {
+        g_msg = e.what();
+        return -1;
+    }
+}
+
+uint64_t* awh_build_knn_graph(const double* m, uint64_t n, uint64_t k, int farthest, uint64_t* out_n) {
+    std::vector<std::vector<double>> dm(n, std::vector<double>(n));
+    for (uint64_t i = 0; i < n; ++i)
+        for (uint64_t j = 0; j < n; ++j) dm[i][j] = m[i * n + j];
+    auto p = build_knn_graph(dm, (size_t)k, farthest != 0);
+    uint64_t* o = (uint64_t*)std::malloc(sizeof(uint64_t) * 2 * (p.size() ? p.size() : 1));
+    for (size_t i = 0; i < p.size(); ++i) {
+        o[2 * i] = p[i].first;
+        o[2 * i + 1] = p[i].second;
+    }
+    *out_n = p.size();
+    return o;
+}
+
+void awh_free(void* p) { std::free(p); }
+}

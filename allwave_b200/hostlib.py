@@ -1,0 +1,76 @@
+"""ctypes binding of liballwave_host.so: C exports (host_capi.cpp) of the C++ host mirror
+(allwave_b200/host/allwave.hpp) of the reference's library surface."""
+import ctypes as C
+import os
+
+from . import _cabi
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_PKG, "liballwave_host.so")
+_lib = None
+
+KIND_NONE, KIND_RANDOM, KIND_AUTO, KIND_CONNECTIVITY, KIND_TREE = range(5)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise ImportError(f"{_SO} is missing: run __graft_entry__.build()")
+        _cabi.lib()  # make sure liballwave_cuda.so is resolvable first
+        L = C.CDLL(_SO)
+        L.awh_last_message.restype = C.c_char_p
+        L.awh_parse_scores.argtypes = [C.c_char_p, C.POINTER(_cabi.AwParams)]
+        L.awh_parse_sparsification.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                               C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.awh_connectivity_probability.argtypes = [C.c_uint64, C.c_double]
+        L.awh_connectivity_probability.restype = C.c_double
+        L.awh_hash_str.argtypes = [C.c_char_p]
+        L.awh_hash_str.restype = C.c_uint64
+        L.awh_mode_from_params.argtypes = [C.POINTER(_cabi.AwParams)]
+        L.awh_pair_list.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), C.c_int, C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.c_int, C.c_int,
+                                    C.POINTER(C.POINTER(C.c_uint64)), C.POINTER(C.c_uint64)]
+        L.awh_build_knn_graph.argtypes = [C.POINTER(C.c_double), C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+        L.awh_build_knn_graph.restype = C.POINTER(C.c_uint64)
+        L.awh_free.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def parse_scores(s):
+    p = _cabi.AwParams()
+    if lib().awh_parse_scores(s.encode(), C.byref(p)) != 0:
+        raise ValueError(lib().awh_last_message().decode())
+    return p
+
+
+def parse_sparsification(s):
+    kind, value, kn, kf, rf, kmer = C.c_int(), C.c_double(), C.c_uint64(), C.c_uint64(), C.c_double(), C.c_int()
+    if lib().awh_parse_sparsification(s.encode(), C.byref(kind), C.byref(value), C.byref(kn), C.byref(kf), C.byref(rf), C.byref(kmer)) != 0:
+        raise ValueError(lib().awh_last_message().decode())
+    return dict(kind=kind.value, value=value.value, k_nearest=kn.value, k_farthest=kf.value, random_fraction=rf.value, kmer_size=kmer.value)
+
+
+def pair_list(ids, kind=KIND_NONE, value=0.0, k_nearest=0, k_farthest=0, random_fraction=0.0, kmer_size=0, exclude_self=True, ctx=None):
+    """AllPairIterator::with_options(...).get_pairs(); ctx (sequences loaded) is required for KIND_TREE"""
+    n = len(ids)
+    ia = (C.c_char_p * max(1, n))(*[i.encode() for i in ids])
+    out = C.POINTER(C.c_uint64)()
+    cnt = C.c_uint64()
+    rc = lib().awh_pair_list(ctx._h if ctx is not None else None, n, ia, kind, value, k_nearest, k_farthest, random_fraction, kmer_size,
+                             1 if exclude_self else 0, C.byref(out), C.byref(cnt))
+    if rc != 0:
+        raise RuntimeError(lib().awh_last_message().decode())
+    pairs = [(out[2 * i], out[2 * i + 1]) for i in range(cnt.value)]
+    lib().awh_free(out)
+    return pairs
+
+
+def build_knn_graph(matrix, k, farthest):
+    n = len(matrix)
+    flat = (C.c_double * max(1, n * n))(*[v for row in matrix for v in row])
+    cnt = C.c_uint64()
+    p = lib().awh_build_knn_graph(flat, n, k, 1 if farthest else 0, C.byref(cnt))
+    out = [(p[2 * i], p[2 * i + 1]) for i in range(cnt.value)]
+    lib().awh_free(p)
+    return out

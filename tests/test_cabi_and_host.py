@@ -112,3 +112,49 @@ def test_partition_world2_gloo():
     assert all_pairs == sorted((i, j) for i in range(16) for j in range(16) if i != j)
     assert out[0][1] == out[1][1] and sum(g[0] for g in out[0][1]) == 240
     assert out[0][2] == out[1][2] == 11.0
+
+
+# ---- C++ host mirror (allwave_b200/host/allwave.hpp) against the oracle ----
+def test_host_pair_lists_match_oracle(oracle):
+    from allwave_b200 import hostlib as H
+
+    ids = ["s%06d" % i for i in range(50)]
+    assert H.pair_list(ids[:3]) == oracle.pair_list(ids[:3], None) and len(H.pair_list(ids[:6])) == 30
+    assert H.pair_list(ids[:4], exclude_self=False) == oracle.pair_list(ids[:4], None, exclude_self=False)
+    assert H.pair_list(ids, H.KIND_RANDOM, 0.3) == oracle.pair_list(ids, None, kind=oracle.SPARS_RANDOM, fraction=0.3)
+    assert H.pair_list(ids, H.KIND_CONNECTIVITY, 0.99) == oracle.pair_list(ids, None, kind=oracle.SPARS_GIANT, fraction=0.99)
+    assert H.pair_list(ids, H.KIND_AUTO) == oracle.pair_list(ids, None, kind=oracle.SPARS_AUTO)
+    L = H.lib()
+    for n in (1, 2, 3, 5, 10, 11, 200, 5000):
+        assert L.awh_connectivity_probability(n, 0.99) == oracle.lib().awo_connectivity_probability(n, 0.99)
+    for s in ("seq1:seq2", "s000000:s000001", ""):
+        assert L.awh_hash_str(s.encode()) == oracle.hash_str(s)
+    m = [[0.0, 0.1, 0.5], [0.1, 0.0, 0.3], [0.5, 0.3, 0.0]]
+    for far in (False, True):
+        assert H.build_knn_graph(m, 1, far) == oracle.build_knn_graph(m, 1, far)
+
+
+def test_host_parsers():
+    from allwave_b200 import hostlib as H
+
+    p = H.parse_scores("0,5,8,2,24,1")
+    assert (p.mismatch_penalty, p.gap_open, p.gap_extend, p.gap2_open, p.gap2_extend, p.has_gap2_open) == (5, 8, 2, 24, 1, 1)
+    assert H.lib().awh_mode_from_params(p) == 2 and H.lib().awh_mode_from_params(H.parse_scores("0,1,1,1")) == 0
+    assert H.lib().awh_mode_from_params(H.parse_scores("0,4,6,2")) == 1
+    with pytest.raises(ValueError, match="Invalid number of scores: 3. Expected 4 or 6 values."):
+        H.parse_scores("0,1,1")
+    with pytest.raises(ValueError, match="Failed to parse scores"):
+        H.parse_scores("0,x,1,1")
+    # the -p grammar and its messages (src/main.rs:136-203)
+    assert H.parse_sparsification("none")["kind"] == H.KIND_NONE and H.parse_sparsification("auto")["kind"] == H.KIND_AUTO
+    assert H.parse_sparsification("giant:0.99") == dict(kind=H.KIND_CONNECTIVITY, value=0.99, k_nearest=0, k_farthest=0, random_fraction=0.0, kmer_size=0)
+    assert H.parse_sparsification("connectivity:0.5")["value"] == 0.5
+    t = H.parse_sparsification("tree:2:1:0.1")
+    assert (t["kind"], t["k_nearest"], t["k_farthest"], t["random_fraction"], t["kmer_size"]) == (H.KIND_TREE, 2, 1, 0.1, 0)
+    assert H.parse_sparsification("tree:3:0:0:21")["kmer_size"] == 21
+    for bad, msg in (("random:0", "Random fraction must be between 0 and 1"), ("random:x", "Invalid random fraction"),
+                     ("giant:1.0", "Giant component probability must be between 0 and 1"), ("tree:0:0:0.1", "At least one of k_nearest"),
+                     ("tree:1:1", "Invalid tree format"), ("tree:1:1:0.1:2", "K-mer size must be between 3 and 31"),
+                     ("tree:1:1:1.5", "Random fraction must be between 0 and 1"), ("bogus", "Invalid sparsification strategy")):
+        with pytest.raises(ValueError, match=msg):
+            H.parse_sparsification(bad)

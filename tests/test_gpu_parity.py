@@ -1,5 +1,6 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI, must equal the CPU oracle
 bit for bit (score, WFA2 op string, PAF line) on the same seeded inputs."""
+import os
 import random
 
 import pytest
@@ -140,3 +141,25 @@ def test_aligner_api(oracle, gpu_ctx):
     st, sc, ops, _ = oracle.wfa_align(oracle.params(), seqs[0], seqs[1])
     assert al.score() == sc and al.cigar() == ops
     al.close()
+
+
+def test_host_tree_pair_list_and_cli(oracle, gpu_ctx, tmp_path):
+    """tree:2:1:0.1 pair list from the C++ host mirror (GPU sketches + Jaccard counts) and the CLI's PAF"""
+    import subprocess
+
+    from allwave_b200 import hostlib as H
+
+    c, ids, seqs, rc = synth.config("C5", n=14, length=1500)
+    gpu_ctx.load_sequences(ids, seqs)
+    got = H.pair_list(ids, H.KIND_TREE, k_nearest=2, k_farthest=1, random_fraction=0.1, ctx=gpu_ctx)
+    exp = oracle.pair_list(ids, seqs, kind=oracle.SPARS_TREE, fraction=0.1, k_nearest=2, k_farthest=1)
+    assert got == exp and len(got) >= 14 * 2
+    fa = tmp_path / "in.fa"
+    fa.write_text("".join(f">{i} extra words\n{s.decode()}\n" for i, s in zip(ids, seqs)))
+    out = tmp_path / "out.paf"
+    exe = os.path.join(os.path.dirname(aw._cabi.so_path()), "allwave")
+    subprocess.check_call([exe, "-i", str(fa), "-o", str(out), "-p", "tree:2:1:0.1", "-s", "0,5,8,2,24,1", "--no-progress"])
+    lines = out.read_text().splitlines()
+    p = oracle.params(**DEFAULT)
+    want = [oracle.align_pair(seqs[q], seqs[t], q, t, p, use_mash=True, qname=ids[q], tname=ids[t])["paf"] for q, t in exp]
+    assert lines == want
