@@ -19,7 +19,7 @@ AW_MEMORY_HIGH, AW_MEMORY_MEDIUM, AW_MEMORY_LOW, AW_MEMORY_ULTRALOW = 0, 1, 2, 3
 
 EXPORTS = [
     "aw_abi_version", "aw_strerror", "aw_last_error", "aw_device_count", "aw_create", "aw_destroy", "aw_set_option",
-    "aw_load_sequences", "aw_num_sequences", "aw_align_pairs", "aw_batch_create", "aw_batch_launch", "aw_batch_fetch",
+    "aw_load_sequences", "aw_num_sequences", "aw_set_orientation_params", "aw_align_pairs", "aw_batch_create", "aw_batch_launch", "aw_batch_fetch",
     "aw_batch_stats", "aw_batch_kernel_ms", "aw_batch_debug_cycles", "aw_batch_destroy", "aw_orient_pairs", "aw_get_sketch", "aw_mash_jaccard_counts",
     "aw_aligner_new_affine", "aw_aligner_new_affine2p", "aw_aligner_set_alignment_scope", "aw_aligner_set_alignment_span",
     "aw_aligner_set_heuristic", "aw_aligner_get_memory_mode", "aw_aligner_align", "aw_aligner_score", "aw_aligner_cigar",
@@ -110,6 +110,7 @@ def lib():
     L.aw_load_sequences.argtypes = [vp, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(C.c_char_p)]
     L.aw_num_sequences.argtypes = [vp]
     L.aw_num_sequences.restype = C.c_uint32
+    L.aw_set_orientation_params.argtypes = [vp, C.POINTER(AwParams)]
     L.aw_align_pairs.argtypes = [vp, C.POINTER(AwParams), C.c_int, C.POINTER(AwPair), C.c_uint64, C.c_uint32, RESULT_CB, vp]
     L.aw_batch_create.argtypes = [vp, C.POINTER(AwParams), C.c_int, C.POINTER(AwPair), C.c_uint64, C.c_uint32, C.POINTER(vp)]
     L.aw_batch_launch.argtypes = [vp, vp, vp]

@@ -99,6 +99,7 @@ struct aw_ctx {
     int64_t chunk_pairs = 65536;
     int band_engine = 0;       // 1 = use the shared-memory diagonal-band engine for phase 1 (experimental)
     int ws16 = 1;              // 1 = int16 wavefront storage when every offset fits
+    aw_params orient_params = {0, 1, 1, 1, 0, 0, 0, 0};  // AlignmentParams::edit_distance(), src/iterator.rs:85
     // sequence store
     uint32_t n = 0;
     std::vector<uint64_t> lens;
@@ -121,7 +122,9 @@ struct aw_batch {
     uint32_t flags = 0;
     uint64_t npairs = 0;
     std::vector<aw_pair> h_pairs;
-    DevBuf d_pairs, d_isrev, d_order, d_out, d_text, d_bytes, d_ctl;  // d_ctl: [0] text cursor, [1] bytes cursor, [2] next_pair
+    DevBuf d_pairs, d_isrev, d_order, d_out, d_text, d_bytes, d_ctl;
+    DevBuf d_out_f, d_out_r, d_strand;  // --wfa-orientation passes: per-strand results and a constant 0.. / 1.. strand array
+    AwPen pen_orient;  // d_ctl: [0] text cursor, [1] bytes cursor, [2] next_pair
     uint64_t text_cap = 0, bytes_cap = 0;
     bool has_order = false;
     uint64_t max_p = 0, max_t = 0;
@@ -245,6 +248,17 @@ extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
 }
 
 extern "C" uint32_t aw_num_sequences(const aw_ctx* c) { return c ? c->n : 0; }
+
+static int pen_from_params(const aw_params* p, AwPen* pen);
+// AllPairIterator::with_orientation_params (src/iterator.rs:95-98)
+extern "C" int aw_set_orientation_params(aw_ctx* c, const aw_params* p) {
+    if (!c || !p) return AW_EINVAL;
+    AwPen pen;
+    int rc = pen_from_params(p, &pen);
+    if (rc) return rc;
+    c->orient_params = *p;
+    return AW_OK;
+}
 
 extern "C" int aw_load_sequences(aw_ctx* c, uint32_t n, const uint8_t* const* seqs, const uint64_t* lens, const char* const* ids) {
     if (!c || (n && (!seqs || !lens))) return AW_EINVAL;
@@ -509,6 +523,9 @@ extern "C" void aw_batch_destroy(aw_ctx* c, aw_batch* b) {
     b->d_text.release();
     b->d_bytes.release();
     b->d_ctl.release();
+    b->d_out_f.release();
+    b->d_out_r.release();
+    b->d_strand.release();
     b->h_out.release();
     b->h_text.release();
     b->h_bytes.release();
@@ -522,15 +539,15 @@ extern "C" int aw_batch_create(aw_ctx* c, const aw_params* params, int orientati
     if (!c || !params || !out || (npairs && !pairs)) return AW_EINVAL;
     *out = nullptr;
     if (npairs > 0xfffffff0ull) return AW_EINVAL;
-    if (orientation_mode == AW_ORIENT_WFA) {
-        aw_set_error("AW_ORIENT_WFA (--wfa-orientation) is not implemented yet");
-        return AW_EUNSUPPORTED;
-    }
-    if (orientation_mode != AW_ORIENT_MASH && orientation_mode != AW_ORIENT_FORWARD) return AW_EINVAL;
+    if (orientation_mode != AW_ORIENT_MASH && orientation_mode != AW_ORIENT_FORWARD && orientation_mode != AW_ORIENT_WFA) return AW_EINVAL;
     AW_CUDA_CHECK(cudaSetDevice(c->device));
     aw_batch* b = new aw_batch();
     int rc = pen_from_params(params, &b->pen);
     if (rc) {
+        delete b;
+        return rc;
+    }
+    if (orientation_mode == AW_ORIENT_WFA && (rc = pen_from_params(&c->orient_params, &b->pen_orient))) {
         delete b;
         return rc;
     }
@@ -558,12 +575,16 @@ extern "C" int aw_batch_create(aw_ctx* c, const aw_params* params, int orientati
     b->bytes_cap = (flags & AW_FLAG_CIGAR_BYTES) ? sum_len + 16 : 16;
     const size_t np1 = (size_t)std::max<uint64_t>(1, npairs);
     if ((rc = b->d_pairs.ensure(sizeof(aw_pair) * np1)) || (rc = b->d_isrev.ensure(np1)) || (rc = b->d_out.ensure(sizeof(AwPairOut) * np1)) ||
-        (rc = b->d_text.ensure(b->text_cap)) || (rc = b->d_bytes.ensure(b->bytes_cap)) || (rc = b->d_ctl.ensure(64))) {
+        (rc = b->d_text.ensure(b->text_cap)) || (rc = b->d_bytes.ensure(b->bytes_cap)) || (rc = b->d_ctl.ensure(64)) ||
+        (orientation_mode == AW_ORIENT_WFA &&
+         ((rc = b->d_out_f.ensure(sizeof(AwPairOut) * np1)) || (rc = b->d_out_r.ensure(sizeof(AwPairOut) * np1)) || (rc = b->d_strand.ensure(2 * np1))))) {
         aw_batch_destroy(c, b);
         return rc;
     }
     cudaError_t e = cudaMemcpyAsync(b->d_pairs.p, pairs, sizeof(aw_pair) * npairs, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(b->d_isrev.p, 0, np1, c->stream);
+    if (e == cudaSuccess && orientation_mode == AW_ORIENT_WFA) e = cudaMemsetAsync(b->d_strand.p, 0, np1, c->stream);
+    if (e == cudaSuccess && orientation_mode == AW_ORIENT_WFA) e = cudaMemsetAsync(b->d_strand.as<uint8_t>() + np1, 1, np1, c->stream);
     if (e == cudaSuccess && varied) {
         // heaviest (longest) pairs first: greedy balance of the persistent CTAs
         std::vector<uint32_t> order(npairs);
@@ -636,8 +657,8 @@ cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bo
 
 // sizes the per-CTA workspace for one launch; attempt 0 is the fast first try, later attempts
 // remove the wavefront-width cap and grow the history arena (retry ladder)
-int plan_launch(aw_ctx* c, const aw_batch* b, uint64_t npairs, uint64_t max_p, uint64_t max_t, int attempt, LaunchCfg* cfg) {
-    const int ncomp = b->pen.two_piece ? 5 : 3;
+int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, uint64_t max_t, int attempt, LaunchCfg* cfg) {
+    const int ncomp = pen.two_piece ? 5 : 3;
     const uint64_t maxlen = std::max(max_p, max_t);
     int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : 256);
     int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : (nt == 128 ? 4 : 2));
@@ -652,14 +673,14 @@ int plan_launch(aw_ctx* c, const aw_batch* b, uint64_t npairs, uint64_t max_p, u
     // int16 storage: every offset (incl. out-of-bounds I/D drift, <= 2*tlen+plen) must stay below 32000
     const bool ws16 = c->ws16 && nt == 256 && (2 * max_t + max_p < 32000) && (2 * max_p + max_t < 32000);
     const uint64_t epi = ws16 ? 2 : 1;  // elements per int
-    uint64_t ring_ints = (2ull * (b->pen.scope + 1) * ncomp * W + epi - 1) / epi;
+    uint64_t ring_ints = (2ull * (pen.scope + 1) * ncomp * W + epi - 1) / epi;
     if (ring_ints >= 0x7f000000ull) {
         aw_set_error("wavefront ring of %llu ints per CTA exceeds the 32-bit workspace index", (unsigned long long)ring_ints);
         return AW_EUNSUPPORTED;
     }
     hist_ints = std::min<uint64_t>(hist_ints, 0x7ff00000ull - ring_ints);
     // int16 band ring (NT=256 kernels): 2 x (scope + BAND_T + 2) slots x ncomp x W halfwords
-    uint64_t ring16_ints = (AW_ENABLE_BAND && c->band_engine && nt == 256 && b->pen.scope <= awk::BAND_MROWS) ? (2ull * (b->pen.scope + awk::BAND_T + 2) * ncomp * W + 1) / 2 + 8 : 0;
+    uint64_t ring16_ints = (AW_ENABLE_BAND && c->band_engine && nt == 256 && pen.scope <= awk::BAND_MROWS) ? (2ull * (pen.scope + awk::BAND_T + 2) * ncomp * W + 1) / 2 + 8 : 0;
     if (ring_ints + ring16_ints >= 0x7f000000ull) ring16_ints = 0;
     hist_ints = std::min<uint64_t>(hist_ints, 0x7ff00000ull - ring_ints - ring16_ints);
     uint64_t ws_ints = ring_ints + hist_ints + ring16_ints;
@@ -690,7 +711,7 @@ int plan_launch(aw_ctx* c, const aw_batch* b, uint64_t npairs, uint64_t max_p, u
     return AW_OK;
 }
 
-void fill_params(aw_ctx* c, aw_batch* b, const LaunchCfg& cfg, awk::KParams* P) {
+void fill_params(aw_ctx* c, aw_batch* b, const AwPen& pen, const LaunchCfg& cfg, awk::KParams* P) {
     memset(P, 0, sizeof(*P));
     P->slots = c->d_slots.as<AwSlot>();
     P->packed = c->d_packed.as<uint32_t>();
@@ -699,7 +720,7 @@ void fill_params(aw_ctx* c, aw_batch* b, const LaunchCfg& cfg, awk::KParams* P) 
     P->id_off = c->d_id_off.as<uint32_t>();
     P->pairs = b->d_pairs.as<aw_pair>();
     P->is_reverse = b->d_isrev.as<uint8_t>();
-    P->pen = b->pen;
+    P->pen = pen;
     P->flags = b->flags;
     P->ws = c->ws_main.as<int>();
     P->ws_ints_per_cta = cfg.ws_ints;
@@ -735,10 +756,42 @@ extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
         ++b->stats[0];
     }
     LaunchCfg cfg;
-    if ((rc = plan_launch(c, b, b->npairs, b->max_p, b->max_t, 0, &cfg))) return rc;
+    if ((rc = plan_launch(c, b->pen, b->npairs, b->max_p, b->max_t, 0, &cfg))) return rc;
     AW_CUDA_CHECK(cudaMemsetAsync(b->d_ctl.p, 0, 64, st));
+    if (b->orient == AW_ORIENT_WFA) {
+        // determine_orientation_wfa: two full alignments with the orientation penalties, forward and
+        // reverse-complemented query, statistics only; then pick the strand with fewer X+I+D columns
+        LaunchCfg cfo;
+        if ((rc = plan_launch(c, b->pen_orient, b->npairs, b->max_p, b->max_t, 0, &cfo))) return rc;  // never larger than the main plan
+        const size_t np1 = (size_t)std::max<uint64_t>(1, b->npairs);
+        for (int strand = 0; strand < 2; ++strand) {
+            awk::KParams Q;
+            fill_params(c, b, b->pen_orient, cfo, &Q);
+            Q.flags = AW_KFLAG_COUNT_ONLY | AW_FLAG_NO_PAF;
+            Q.is_reverse = b->d_strand.as<uint8_t>() + strand * np1;
+            Q.order = b->has_order ? b->d_order.as<uint32_t>() : nullptr;
+            Q.npairs = (uint32_t)b->npairs;
+            Q.next_pair = reinterpret_cast<unsigned int*>(b->d_ctl.as<unsigned long long>() + 3 + strand);
+            Q.out = (strand == 0 ? b->d_out_f : b->d_out_r).as<AwPairOut>();
+            Q.text = b->d_text.as<char>();
+            Q.text_cursor = b->d_ctl.as<unsigned long long>() + 5;
+            Q.text_cap = b->text_cap;
+            Q.bytes = b->d_bytes.as<uint8_t>();
+            Q.bytes_cursor = b->d_ctl.as<unsigned long long>() + 6;
+            Q.bytes_cap = b->bytes_cap;
+            cudaError_t eo = dispatch_align(Q, cfo.nt, c->all_clean ? 2 : 8, b->pen_orient.two_piece != 0, cfo.ws16, cfo.grid, st);
+            if (eo != cudaSuccess) {
+                aw_set_error("orientation kernel launch: %s", cudaGetErrorString(eo));
+                return AW_ECUDA;
+            }
+            ++b->stats[0];
+        }
+        awk::aw_wfa_orient_pick_kernel<<<c->sm_count * 4, 256, 0, st>>>(b->d_out_f.as<AwPairOut>(), b->d_out_r.as<AwPairOut>(), b->npairs, b->d_isrev.as<uint8_t>());
+        AW_CUDA_CHECK(cudaGetLastError());
+        ++b->stats[0];
+    }
     awk::KParams P;
-    fill_params(c, b, cfg, &P);
+    fill_params(c, b, b->pen, cfg, &P);
     P.order = b->has_order ? b->d_order.as<uint32_t>() : nullptr;
     P.npairs = (uint32_t)b->npairs;
     P.next_pair = reinterpret_cast<unsigned int*>(b->d_ctl.as<unsigned long long>() + 2);
@@ -782,7 +835,7 @@ static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
             idlen_max = std::max(idlen_max, c->ids[b->h_pairs[i].query_idx].size() + c->ids[b->h_pairs[i].target_idx].size());
         }
         LaunchCfg cfg;
-        int rc = plan_launch(c, b, failed.size(), max_p, max_t, attempt, &cfg);
+        int rc = plan_launch(c, b->pen, failed.size(), max_p, max_t, attempt, &cfg);
         if (rc) return rc;
         const uint64_t text_cap = 12 * sum_len + (256 + idlen_max) * failed.size() + 1024;
         const uint64_t bytes_cap = (b->flags & AW_FLAG_CIGAR_BYTES) ? sum_len + 16 : 16;
@@ -793,7 +846,7 @@ static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
         cudaError_t e = cudaMemcpy(d_order.p, failed.data(), 4 * failed.size(), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemset(d_ctl.p, 0, 64);
         awk::KParams P;
-        fill_params(c, b, cfg, &P);
+        fill_params(c, b, b->pen, cfg, &P);
         P.order = d_order.as<uint32_t>();
         P.npairs = (uint32_t)failed.size();
         P.next_pair = reinterpret_cast<unsigned int*>(d_ctl.as<unsigned long long>() + 2);

@@ -273,6 +273,16 @@ __global__ void aw_orient_kernel(const aw_pair* __restrict__ pairs, uint64_t npa
     }
 }
 
+// determine_orientation_wfa (src/alignment.rs:157-175): compare the X+I+D column counts of the two
+// orientation alignments; fwd <= rev keeps the forward strand; a failed alignment counts as usize::MAX
+__global__ void aw_wfa_orient_pick_kernel(const AwPairOut* __restrict__ fwd, const AwPairOut* __restrict__ rev, uint64_t npairs, uint8_t* __restrict__ is_reverse) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < npairs; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long f = fwd[i].status == AW_OK ? fwd[i].n_x + fwd[i].n_i + fwd[i].n_d : ~0ull;
+        const unsigned long long r = rev[i].status == AW_OK ? rev[i].n_x + rev[i].n_i + rev[i].n_d : ~0ull;
+        is_reverse[i] = (f <= r) ? 0 : 1;
+    }
+}
+
 // all-pairs canonical Jaccard counts, i<j (src/mash.rs:156-162); one warp per (i,j)
 __global__ void aw_jaccard_matrix_kernel(uint32_t n, const uint64_t* __restrict__ sk, const uint32_t* __restrict__ sk_n, uint32_t sketch_size,
                                          uint32_t* __restrict__ inter, uint32_t* __restrict__ uni) {

@@ -15,6 +15,7 @@
 
 namespace awk {
 
+#define AW_KFLAG_COUNT_ONLY 0x100u  // internal: statistics only (orientation passes), no text output
 constexpr int NRED = 16;       // reduction slots, see RED_* below
 constexpr int MAX_STACK = 96;  // DFS depth bound of the biWFA recursion
 constexpr int HIST_META_INTS = 16;
@@ -1674,11 +1675,12 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
         const uint32_t qid0 = P.id_off[pr.query_idx], qid1 = P.id_off[pr.query_idx + 1];
         const uint32_t tid0 = P.id_off[pr.target_idx], tid1 = P.id_off[pr.target_idx + 1];
         const bool want_paf = !(P.flags & AW_FLAG_NO_PAF);
+        const bool count_only = (P.flags & AW_KFLAG_COUNT_ONLY) != 0;
         // header: q qlen qs qe strand t tlen ts te matches block 60 gi:f:x.xxxxxx cg:Z:
         const unsigned hdr_len = (qid1 - qid0) + 1 + ndigits(PLEN) + 1 + 1 + 1 + ndigits(q_end) + 1 + 1 + 1 + (tid1 - tid0) + 1 + ndigits(TLEN) + 1 + 1 + 1 +
                                  ndigits(t_end) + 1 + ndigits(n_m) + 1 + ndigits(block_len) + 1 + 2 + 1 + 5 + 8 + 1 + 5;
-        const unsigned long long line_len = want_paf ? hdr_len + cg_len : cg_len;
-        const unsigned long long nbytes = (P.flags & AW_FLAG_CIGAR_BYTES) ? (n_m + n_x + n_i + n_d) : 0;
+        const unsigned long long line_len = count_only ? 0 : (want_paf ? hdr_len + cg_len : cg_len);
+        const unsigned long long nbytes = (!count_only && (P.flags & AW_FLAG_CIGAR_BYTES)) ? (n_m + n_x + n_i + n_d) : 0;
         if (tid == 0) {
             s_text_off = atomicAdd(P.text_cursor, line_len);
             s_bytes_off = nbytes ? atomicAdd(P.bytes_cursor, nbytes) : 0ull;
@@ -1686,7 +1688,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_
         cta_sync<NT>();
         const unsigned long long text_off = s_text_off, bytes_off = s_bytes_off;
         if (status == ST_OK && (text_off + line_len > P.text_cap || bytes_off + nbytes > P.bytes_cap)) status = ST_FAIL_WORKSPACE;
-        if (status == ST_OK) {
+        if (status == ST_OK && !count_only) {
             char* line = P.text + text_off;
             char* cg = line;
             if (want_paf) {

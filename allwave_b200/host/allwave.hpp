@@ -437,6 +437,11 @@ class AllPairIterator {
             cp[i].target_idx = (uint32_t)pairs_[first + i].second;
         }
         const aw_params p = params_.to_c();
+        if (!use_mash_) {
+            const aw_params op = orientation_params_.to_c();
+            int rco = aw_set_orientation_params(ctx_.get(), &op);
+            if (rco != AW_OK) throw std::runtime_error(std::string("aw_set_orientation_params: ") + aw_strerror(rco) + ": " + aw_last_error());
+        }
         Trampoline t{&cb, nullptr, flags};
         int rc = aw_align_pairs(ctx_.get(), &p, use_mash_ ? AW_ORIENT_MASH : AW_ORIENT_WFA, cp.data(), count, flags, &c_callback, &t);
         if (t.err) std::rethrow_exception(t.err);

@@ -116,6 +116,9 @@ int aw_set_option(aw_ctx* ctx, const char* key, int64_t value);
 int aw_load_sequences(aw_ctx* ctx, uint32_t n, const uint8_t* const* seqs, const uint64_t* lens,
                       const char* const* ids);
 uint32_t aw_num_sequences(const aw_ctx* ctx);
+/* penalties of the two orientation alignments of AW_ORIENT_WFA (AllPairIterator::with_orientation_params,
+ * src/iterator.rs:95-98); default AlignmentParams::edit_distance() = 0,1,1,1 */
+int aw_set_orientation_params(aw_ctx* ctx, const aw_params* params);
 
 /* ---- the hot path, host-facing: align a pair list, stream results to a callback ---- */
 int aw_align_pairs(aw_ctx* ctx, const aw_params* params, int orientation_mode, const aw_pair* pairs,

@@ -163,3 +163,15 @@ def test_host_tree_pair_list_and_cli(oracle, gpu_ctx, tmp_path):
     p = oracle.params(**DEFAULT)
     want = [oracle.align_pair(seqs[q], seqs[t], q, t, p, use_mash=True, qname=ids[q], tname=ids[t])["paf"] for q, t in exp]
     assert lines == want
+
+
+def test_wfa_orientation(oracle, gpu_ctx):
+    """--wfa-orientation (src/alignment.rs:157-175): two edit-distance alignments decide the strand"""
+    c, ids, seqs, rc = synth.config("C5", n=6, length=1200)
+    gpu_ctx.load_sequences(ids, seqs)
+    pairs = _all_pairs(6)
+    res = gpu_ctx.align_pairs(aw.make_params(**DEFAULT), pairs, orientation=aw.AW_ORIENT_WFA)
+    p = oracle.params(**DEFAULT)
+    for r, (q, t) in zip(res, pairs):
+        o = oracle.align_pair(seqs[q], seqs[t], q, t, p, use_mash=False, qname=ids[q], tname=ids[t])
+        assert r["is_reverse"] == bool(o["is_reverse"]) == (rc[q] != rc[t]) and r["paf"] == o["paf"] and r["score"] == o["score"]
