@@ -661,7 +661,7 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     const int ncomp = pen.two_piece ? 5 : 3;
     const uint64_t maxlen = std::max(max_p, max_t);
     int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : 256);
-    int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : (nt == 128 ? 4 : 2));
+    int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : 4);  // must match AW_CTAS_PER_SM_256
     uint64_t full_w = max_p + max_t + 3;
     uint64_t W = full_w;
     if (attempt == 0 && W > (uint64_t)c->max_w) W = (uint64_t)c->max_w;

@@ -16,6 +16,9 @@
 namespace awk {
 
 #define AW_KFLAG_COUNT_ONLY 0x100u  // internal: statistics only (orientation passes), no text output
+#ifndef AW_CTAS_PER_SM_256
+#define AW_CTAS_PER_SM_256 4  // resident 256-thread CTAs per SM the register budget is planned for (measured best: 4 x 64 regs)
+#endif
 constexpr int NRED = 16;       // reduction slots, see RED_* below
 constexpr int MAX_STACK = 96;  // DFS depth bound of the biWFA recursion
 constexpr int HIST_META_INTS = 16;
@@ -259,21 +262,12 @@ __device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7],
     int m_hi = INT_MIN, m_lo = INT_MIN, akM = INT_MIN, akAll = INT_MIN, endval = INT_MIN;
     int i1_hi = INT_MIN, i1_lo = INT_MIN, d1_hi = INT_MIN, d1_lo = INT_MIN;
     int i2_hi = INT_MIN, i2_lo = INT_MIN, d2_hi = INT_MIN, d2_lo = INT_MIN;
-    // running pointers: one per input / output array, advanced by NT per iteration, so the loop
-    // body addresses everything with immediate offsets (no per-access 64-bit arithmetic)
+    // one running base pointer (ws + k) plus a 32-bit element offset per input / output array
     const int k0 = lo + tid;
-    const WS* p_mx = ws + in[IN_MX].off + k0;
-    const WS* p_mo1 = ws + in[IN_MO1].off + k0;
-    const WS* p_i1e = ws + in[IN_I1E].off + k0;
-    const WS* p_d1e = ws + in[IN_D1E].off + k0;
-    const WS* p_mo2 = ws + in[IN_MO2].off + k0;
-    const WS* p_i2e = ws + in[IN_I2E].off + k0;
-    const WS* p_d2e = ws + in[IN_D2E].off + k0;
-    WS* q_m = ws + out[AW_COMP_M] + k0;
-    WS* q_i1 = ws + out[AW_COMP_I1] + k0;
-    WS* q_d1 = ws + out[AW_COMP_D1] + k0;
-    WS* q_i2 = ws + out[AW_COMP_I2] + k0;
-    WS* q_d2 = ws + out[AW_COMP_D2] + k0;
+    WS* pk = ws + k0;
+    const int o_mx = in[IN_MX].off, o_mo1 = in[IN_MO1].off, o_i1e = in[IN_I1E].off, o_d1e = in[IN_D1E].off;
+    const int o_mo2 = in[IN_MO2].off, o_i2e = in[IN_I2E].off, o_d2e = in[IN_D2E].off;
+    const int w_m = out[AW_COMP_M], w_i1 = out[AW_COMP_I1], w_d1 = out[AW_COMP_D1], w_i2 = out[AW_COMP_I2], w_d2 = out[AW_COMP_D2];
     // one cell: recurrences, bounds, extend, stores, trim / antidiagonal tracking
     auto cell = [&](int k, int j, int mo1l, int mo1r, int i1l, int d1r, int mo2l, int mo2r, int i2l, int d2r, int mx) {
         const int i1 = max(mo1l, i1l) + 1;
@@ -294,12 +288,13 @@ __device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7],
             m_hi = k;
             akM = max(akM, 2 * m - k);
         }
-        q_m[j * NT] = to_ws<WS>(m);
-        q_i1[j * NT] = to_ws<WS>(i1);
-        q_d1[j * NT] = to_ws<WS>(d1);
+        (void)j;
+        pk[w_m] = to_ws<WS>(m);
+        pk[w_i1] = to_ws<WS>(i1);
+        pk[w_d1] = to_ws<WS>(d1);
         if (TWO) {
-            q_i2[j * NT] = to_ws<WS>(i2);
-            q_d2[j * NT] = to_ws<WS>(d2);
+            pk[w_i2] = to_ws<WS>(i2);
+            pk[w_d2] = to_ws<WS>(d2);
         }
         if (narrow || k - lo < EDGE_ZONE || hi - k < EDGE_ZONE) {
             // wavefront_compute_trim_ends keeps [first, last] in-bounds cell of every component
@@ -324,53 +319,37 @@ __device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7],
         }
         if (k == k_end) endval = (comp_end == AW_COMP_M) ? m : (comp_end == AW_COMP_I1) ? i1 : (comp_end == AW_COMP_D1) ? d1 : (comp_end == AW_COMP_I2) ? i2 : d2;
     };
-    auto advance = [&](int n) {
-        p_mx += n;
-        p_mo1 += n;
-        p_i1e += n;
-        p_d1e += n;
-        q_m += n;
-        q_i1 += n;
-        q_d1 += n;
-        if (TWO) {
-            p_mo2 += n;
-            p_i2e += n;
-            p_d2e += n;
-            q_i2 += n;
-            q_d2 += n;
-        }
-    };
     int k = k0;
     for (; k <= hi; k += NT) {
         int mo1l, mo1r, i1l, d1r, mo2l = AW_NULLV, mo2r = AW_NULLV, i2l = AW_NULLV, d2r = AW_NULLV, mx;
         if (k >= fast_lo && k <= fast_hi) {  // interior: immediate-offset loads, no checks
-            mo1l = p_mo1[-1];
-            mo1r = p_mo1[1];
-            i1l = p_i1e[-1];
-            d1r = p_d1e[1];
+            mo1l = pk[o_mo1 - 1];
+            mo1r = pk[o_mo1 + 1];
+            i1l = pk[o_i1e - 1];
+            d1r = pk[o_d1e + 1];
             if (TWO) {
-                mo2l = p_mo2[-1];
-                mo2r = p_mo2[1];
-                i2l = p_i2e[-1];
-                d2r = p_d2e[1];
+                mo2l = pk[o_mo2 - 1];
+                mo2r = pk[o_mo2 + 1];
+                i2l = pk[o_i2e - 1];
+                d2r = pk[o_d2e + 1];
             }
-            mx = p_mx[0];
+            mx = pk[o_mx];
         } else {
-            auto ck = [&](const In& w, const WS* p, int d) -> int { return (k + d >= w.lo && k + d <= w.hi) ? (int)p[d] : AW_NULLV; };
-            mo1l = ck(in[IN_MO1], p_mo1, -1);
-            mo1r = ck(in[IN_MO1], p_mo1, 1);
-            i1l = ck(in[IN_I1E], p_i1e, -1);
-            d1r = ck(in[IN_D1E], p_d1e, 1);
+            auto ck = [&](const In& w, int o, int d) -> int { return (k + d >= w.lo && k + d <= w.hi) ? (int)pk[o + d] : AW_NULLV; };
+            mo1l = ck(in[IN_MO1], o_mo1, -1);
+            mo1r = ck(in[IN_MO1], o_mo1, 1);
+            i1l = ck(in[IN_I1E], o_i1e, -1);
+            d1r = ck(in[IN_D1E], o_d1e, 1);
             if (TWO) {
-                mo2l = ck(in[IN_MO2], p_mo2, -1);
-                mo2r = ck(in[IN_MO2], p_mo2, 1);
-                i2l = ck(in[IN_I2E], p_i2e, -1);
-                d2r = ck(in[IN_D2E], p_d2e, 1);
+                mo2l = ck(in[IN_MO2], o_mo2, -1);
+                mo2r = ck(in[IN_MO2], o_mo2, 1);
+                i2l = ck(in[IN_I2E], o_i2e, -1);
+                d2r = ck(in[IN_D2E], o_d2e, 1);
             }
-            mx = ck(in[IN_MX], p_mx, 0);
+            mx = ck(in[IN_MX], o_mx, 0);
         }
         cell(k, 0, mo1l, mo1r, i1l, d1r, mo2l, mo2r, i2l, d2r, mx);
-        advance(NT);
+        pk += NT;
     }
     red_max<NT>(red, RED_HI + AW_COMP_M, m_hi);
     red_max<NT>(red, RED_LO + AW_COMP_M, m_lo);
@@ -527,7 +506,7 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
 // The kernel
 // ------------------------------------------------------------------------------------------
 template <int NT, int BITS, bool TWO, class WS>
-__global__ void __launch_bounds__(NT, (NT >= 256) ? 2 : (NT == 128 ? 4 : 1)) aw_align_kernel(const KParams P) {
+__global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 128 ? 4 : 1)) aw_align_kernel(const KParams P) {
     constexpr int NCOMP = TWO ? 5 : 3;
     extern __shared__ unsigned long long smem_raw[];
     const int scope = P.pen.scope;
