@@ -259,9 +259,16 @@ __device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7],
         }
     }
     const bool narrow = (hi - lo) < 2 * EDGE_ZONE;
-    int m_hi = INT_MIN, m_lo = INT_MIN, akM = INT_MIN, akAll = INT_MIN, endval = INT_MIN;
-    int i1_hi = INT_MIN, i1_lo = INT_MIN, d1_hi = INT_MIN, d1_lo = INT_MIN;
-    int i2_hi = INT_MIN, i2_lo = INT_MIN, d2_hi = INT_MIN, d2_lo = INT_MIN;
+    int akM = INT_MIN, akAll = INT_MIN;
+    // in-bounds ends of one component inside an edge row: one ballot, the leader lane publishes both ends
+    auto edge_track = [&](int c, bool inb, int krow) {
+        const unsigned amask = __activemask();
+        const unsigned mask = __ballot_sync(amask, inb);
+        if (mask != 0 && (int)(tid & 31) == __ffs(amask) - 1) {
+            atomicMax(&red[RED_HI + c], krow + 31 - __clz(mask));
+            atomicMax(&red[RED_LO + c], -(krow + __ffs(mask) - 1));
+        }
+    };
     // one running base pointer (ws + k) plus a 32-bit element offset per input / output array
     const int k0 = lo + tid;
     WS* pk = ws + k0;
@@ -284,8 +291,6 @@ __device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7],
         if ((unsigned)m > tlen || (unsigned)(m - k) > plen) m = AW_NULLV;
         if (m >= 0) {
             m = extend_cell<BITS>(sv, k, m);
-            if (m_lo == INT_MIN) m_lo = -k;
-            m_hi = k;
             akM = max(akM, 2 * m - k);
         }
         (void)j;
@@ -296,28 +301,19 @@ __device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7],
             pk[w_i2] = to_ws<WS>(i2);
             pk[w_d2] = to_ws<WS>(d2);
         }
-        if (narrow || k - lo < EDGE_ZONE || hi - k < EDGE_ZONE) {
-            // wavefront_compute_trim_ends keeps [first, last] in-bounds cell of every component
-            if ((unsigned)i1 <= tlen && (unsigned)(i1 - k) <= plen) {
-                if (i1_lo == INT_MIN) i1_lo = -k;
-                i1_hi = k;
-            }
-            if ((unsigned)d1 <= tlen && (unsigned)(d1 - k) <= plen) {
-                if (d1_lo == INT_MIN) d1_lo = -k;
-                d1_hi = k;
-            }
+        // wavefront_compute_trim_ends keeps [first, last] in-bounds cell of every component: only rows
+        // (32 consecutive diagonals of one warp) that touch an edge zone can hold those ends
+        const int krow = k - (int)(tid & 31);
+        if (narrow || krow - lo < EDGE_ZONE || hi - (krow + 31) < EDGE_ZONE) {
+            edge_track(AW_COMP_M, m >= 0, krow);
+            edge_track(AW_COMP_I1, (unsigned)i1 <= tlen && (unsigned)(i1 - k) <= plen, krow);
+            edge_track(AW_COMP_D1, (unsigned)d1 <= tlen && (unsigned)(d1 - k) <= plen, krow);
             if (TWO) {
-                if ((unsigned)i2 <= tlen && (unsigned)(i2 - k) <= plen) {
-                    if (i2_lo == INT_MIN) i2_lo = -k;
-                    i2_hi = k;
-                }
-                if ((unsigned)d2 <= tlen && (unsigned)(d2 - k) <= plen) {
-                    if (d2_lo == INT_MIN) d2_lo = -k;
-                    d2_hi = k;
-                }
+                edge_track(AW_COMP_I2, (unsigned)i2 <= tlen && (unsigned)(i2 - k) <= plen, krow);
+                edge_track(AW_COMP_D2, (unsigned)d2 <= tlen && (unsigned)(d2 - k) <= plen, krow);
             }
         }
-        if (k == k_end) endval = (comp_end == AW_COMP_M) ? m : (comp_end == AW_COMP_I1) ? i1 : (comp_end == AW_COMP_D1) ? d1 : (comp_end == AW_COMP_I2) ? i2 : d2;
+        if (k == k_end) red[RED_END] = (comp_end == AW_COMP_M) ? m : (comp_end == AW_COMP_I1) ? i1 : (comp_end == AW_COMP_D1) ? d1 : (comp_end == AW_COMP_I2) ? i2 : d2;
     };
     int k = k0;
     for (; k <= hi; k += NT) {
@@ -351,21 +347,8 @@ __device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7],
         cell(k, 0, mo1l, mo1r, i1l, d1r, mo2l, mo2r, i2l, d2r, mx);
         pk += NT;
     }
-    red_max<NT>(red, RED_HI + AW_COMP_M, m_hi);
-    red_max<NT>(red, RED_LO + AW_COMP_M, m_lo);
     red_max<NT>(red, RED_AKM, akM);
     red_max<NT>(red, RED_AKALL, akAll);
-    red_max<NT>(red, RED_HI + AW_COMP_I1, i1_hi);
-    red_max<NT>(red, RED_LO + AW_COMP_I1, i1_lo);
-    red_max<NT>(red, RED_HI + AW_COMP_D1, d1_hi);
-    red_max<NT>(red, RED_LO + AW_COMP_D1, d1_lo);
-    if (TWO) {
-        red_max<NT>(red, RED_HI + AW_COMP_I2, i2_hi);
-        red_max<NT>(red, RED_LO + AW_COMP_I2, i2_lo);
-        red_max<NT>(red, RED_HI + AW_COMP_D2, d2_hi);
-        red_max<NT>(red, RED_LO + AW_COMP_D2, d2_lo);
-    }
-    red_max<NT>(red, RED_END, endval);
 }
 
 // after the barrier: trimmed ranges (wavefront_compute_trim_ends) from the reductions
@@ -384,12 +367,12 @@ __device__ __forceinline__ void wf_finish(const int* red, int lo, int hi, StepOu
         if (h == INT_MIN) {  // nothing in bounds (among the tracked cells)
             so.lo[c] = lo;
             so.hi[c] = lo - 1;
-            if (c != AW_COMP_M && !narrow) so.ambiguous = true;
+            if (!narrow) so.ambiguous = true;
         } else {
             so.lo[c] = -l;
             so.hi[c] = h;
             // exact only if each end was found inside its tracked zone
-            if (c != AW_COMP_M && !narrow && ((-l) - lo >= EDGE_ZONE || hi - h >= EDGE_ZONE)) so.ambiguous = true;
+            if (!narrow && ((-l) - lo >= EDGE_ZONE || hi - h >= EDGE_ZONE)) so.ambiguous = true;
         }
     }
     so.akM = red[RED_AKM];
@@ -397,7 +380,7 @@ __device__ __forceinline__ void wf_finish(const int* red, int lo, int hi, StepOu
     so.endval = red[RED_END];
 }
 
-// exact trim of every I/D component by re-reading the stored wavefront (rare slow path)
+// exact trim of every component by re-reading the stored wavefront (rare slow path)
 template <int NT, bool TWO, class WS>
 __device__ __noinline__ void wf_rescan(const WS* __restrict__ ws, const int (&out)[5], int lo, int hi, int plen_, int tlen_, int* red, StepOut& so) {
     const unsigned tlen = (unsigned)tlen_, plen = (unsigned)plen_;
@@ -409,7 +392,7 @@ __device__ __noinline__ void wf_rescan(const WS* __restrict__ ws, const int (&ou
     for (int c = 0; c < 5; ++c) vhi[c] = vlo[c] = INT_MIN;
     for (int k = lo + (int)threadIdx.x; k <= hi; k += NT) {
 #pragma unroll
-        for (int c = 1; c < 5; ++c) {
+        for (int c = 0; c < 5; ++c) {
             if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
             const int v = ws[out[c] + k];
             if ((unsigned)v <= tlen && (unsigned)(v - k) <= plen) {
@@ -419,14 +402,14 @@ __device__ __noinline__ void wf_rescan(const WS* __restrict__ ws, const int (&ou
         }
     }
 #pragma unroll
-    for (int c = 1; c < 5; ++c) {
+    for (int c = 0; c < 5; ++c) {
         if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
         red_max<NT>(red, RED_HI + c, vhi[c]);
         red_max<NT>(red, RED_LO + c, vlo[c]);
     }
     cta_sync<NT>();
 #pragma unroll
-    for (int c = 1; c < 5; ++c) {
+    for (int c = 0; c < 5; ++c) {
         if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
         const int h = red[RED_HI + c], l = red[RED_LO + c];
         if (h == INT_MIN) {
