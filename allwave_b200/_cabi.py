@@ -94,9 +94,11 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_SO):
-        raise ImportError(f"{_SO} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
-    L = C.CDLL(_SO)
+    # dev aid: ALLWAVE_CUDA_LIB selects another build of the same library (kernel tuning variants)
+    _so = os.environ.get("ALLWAVE_CUDA_LIB", _SO)
+    if not os.path.exists(_so):
+        raise ImportError(f"{_so} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (no CPU fallback exists)")
+    L = C.CDLL(_so)
     vp = C.c_void_p
     L.aw_abi_version.restype = C.c_int
     L.aw_strerror.argtypes = [C.c_int]

@@ -236,7 +236,7 @@ extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
     std::string k(key);
     if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
     else if (k == "threads_per_cta") {
-        if (value != 0 && value != 32 && value != 256) return AW_EINVAL;
+        if (value != 0 && value != 32 && value != 128 && value != 256) return AW_EINVAL;
         c->threads_per_cta = (int)value;
     } else if (k == "max_wavefront_width") c->max_w = value;
     else if (k == "hist_mb") c->hist_mb = value;
@@ -617,7 +617,6 @@ struct LaunchCfg {
     int nt, grid;
     int W;
     unsigned long long ws_ints, hist_ints, runs_cap;
-    long long ring16_off;
     bool ws16;
     int hist_max_scores;
 };
@@ -636,9 +635,9 @@ cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStrea
 cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bool ws16, int grid, cudaStream_t st) {
     const int scope = P.pen.scope;
     size_t smem = sizeof(awk::SlotMeta) * 2 * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt;
-    if (nt == 256 && P.ring16_int_off >= 0) smem += awk::band_smem_bytes(scope);  // band engine enabled
 #define AW_CASE(NT_, BITS_, TWO_, WS_, W16_) \
     if (nt == NT_ && bits == BITS_ && two == TWO_ && ws16 == W16_) return launch_align<NT_, BITS_, TWO_, WS_>(P, grid, smem, st);
+#ifndef AW_FAST_BUILD  // dev builds (-DAW_FAST_BUILD) keep only the two-piece 2-bit int16 kernels
     AW_CASE(32, 2, true, int, false)
     AW_CASE(32, 2, false, int, false)
     AW_CASE(32, 8, true, int, false)
@@ -647,10 +646,19 @@ cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bo
     AW_CASE(256, 2, false, int, false)
     AW_CASE(256, 8, true, int, false)
     AW_CASE(256, 8, false, int, false)
-    AW_CASE(256, 2, true, short, true)
     AW_CASE(256, 2, false, short, true)
     AW_CASE(256, 8, true, short, true)
     AW_CASE(256, 8, false, short, true)
+    AW_CASE(128, 2, false, short, true)
+    AW_CASE(128, 8, true, short, true)
+    AW_CASE(128, 8, false, short, true)
+    AW_CASE(128, 2, true, int, false)
+    AW_CASE(128, 2, false, int, false)
+    AW_CASE(128, 8, true, int, false)
+    AW_CASE(128, 8, false, int, false)
+#endif
+    AW_CASE(256, 2, true, short, true)
+    AW_CASE(128, 2, true, short, true)
 #undef AW_CASE
     return cudaErrorInvalidValue;
 }
@@ -661,29 +669,27 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     const int ncomp = pen.two_piece ? 5 : 3;
     const uint64_t maxlen = std::max(max_p, max_t);
     int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : 256);
-    int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : 4);  // must match AW_CTAS_PER_SM_256
-    uint64_t full_w = max_p + max_t + 3;
+    int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : AW_CTAS_PER_SM(nt));
+    uint64_t full_w = (max_p + max_t + 3 + 16 + 15) & ~15ull;  // rows are 16-element aligned (vectorised int16 loop)
     uint64_t W = full_w;
-    if (attempt == 0 && W > (uint64_t)c->max_w) W = (uint64_t)c->max_w;
+    if (attempt == 0 && W > (uint64_t)c->max_w) W = std::max<uint64_t>(32, (uint64_t)c->max_w & ~15ull);
     uint64_t hist_ints = (uint64_t)c->hist_mb * (1u << 20) / 4;
     if (nt == 32 && attempt == 0) hist_ints = std::min<uint64_t>(hist_ints, 1u << 18);
     for (int a = 0; a < attempt; ++a) hist_ints *= 8;
     int hist_max_scores = attempt == 0 ? (nt == 32 ? 1024 : 4096) : (attempt == 1 ? 32768 : 262144);
     uint64_t runs_cap = max_p + max_t + 4;
     // int16 storage: every offset (incl. out-of-bounds I/D drift, <= 2*tlen+plen) must stay below 32000
-    const bool ws16 = c->ws16 && nt == 256 && (2 * max_t + max_p < 32000) && (2 * max_p + max_t < 32000);
+    const bool ws16 = c->ws16 && nt >= 64 && (2 * max_t + max_p < 32000) && (2 * max_p + max_t < 32000);
     const uint64_t epi = ws16 ? 2 : 1;  // elements per int
-    uint64_t ring_ints = (2ull * (pen.scope + 1) * ncomp * W + epi - 1) / epi;
+    uint64_t ring_ints = ((2ull * (pen.scope + 1) * ncomp + 1) * W + epi - 1) / epi;  // + the all-NULL row of the int16 path
     if (ring_ints >= 0x7f000000ull) {
         aw_set_error("wavefront ring of %llu ints per CTA exceeds the 32-bit workspace index", (unsigned long long)ring_ints);
         return AW_EUNSUPPORTED;
     }
     hist_ints = std::min<uint64_t>(hist_ints, 0x7ff00000ull - ring_ints);
-    // int16 band ring (NT=256 kernels): 2 x (scope + BAND_T + 2) slots x ncomp x W halfwords
-    uint64_t ring16_ints = (AW_ENABLE_BAND && c->band_engine && nt == 256 && pen.scope <= awk::BAND_MROWS) ? (2ull * (pen.scope + awk::BAND_T + 2) * ncomp * W + 1) / 2 + 8 : 0;
-    if (ring_ints + ring16_ints >= 0x7f000000ull) ring16_ints = 0;
-    hist_ints = std::min<uint64_t>(hist_ints, 0x7ff00000ull - ring_ints - ring16_ints);
-    uint64_t ws_ints = ring_ints + hist_ints + ring16_ints;
+    hist_ints &= ~7ull;
+    ring_ints = (ring_ints + 7) & ~7ull;
+    uint64_t ws_ints = ring_ints + hist_ints;
     uint64_t per_cta = ws_ints * 4 + (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 + runs_cap * 8;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return AW_ECUDA;
@@ -699,7 +705,6 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     cfg->grid = (int)grid;
     cfg->W = (int)std::min<uint64_t>(W, 0x7ffffff0ull);
     cfg->ws_ints = ws_ints;
-    cfg->ring16_off = ring16_ints ? (long long)(ring_ints + hist_ints) : -1;
     cfg->hist_ints = hist_ints * epi;  // capacity in workspace elements
     cfg->ws16 = ws16;
     cfg->runs_cap = runs_cap;
@@ -726,7 +731,6 @@ void fill_params(aw_ctx* c, aw_batch* b, const AwPen& pen, const LaunchCfg& cfg,
     P->ws_ints_per_cta = cfg.ws_ints;
     P->W = cfg.W;
     P->hist_ints = (int)std::min<unsigned long long>(cfg.hist_ints, 0x7fffffffull);
-    P->ring16_int_off = cfg.ring16_off;
     P->ws_hist_meta = c->ws_hist_meta.as<int>();
     P->hist_max_scores = cfg.hist_max_scores;
     P->ws_runs = c->ws_runs.as<uint32_t>();

@@ -16,43 +16,38 @@
 namespace awk {
 
 #define AW_KFLAG_COUNT_ONLY 0x100u  // internal: statistics only (orientation passes), no text output
-#ifndef AW_CTAS_PER_SM_256
-#define AW_CTAS_PER_SM_256 4  // resident 256-thread CTAs per SM the register budget is planned for (measured best: 4 x 64 regs)
+#ifndef AW_CPT
+#define AW_CPT 8
 #endif
-constexpr int NRED = 16;       // reduction slots, see RED_* below
+#ifndef AW_REGS
+#define AW_REGS 128  // register budget per thread of the CTA-per-pair kernels: resident CTAs per SM = 65536 / (NT * AW_REGS)
+#endif
+#define AW_CTAS_PER_SM(NT) ((NT) == 32 ? 1 : (65536 / ((NT) * AW_REGS)))
+constexpr int NRED = 20;       // reduction slots, see RED_* below
 constexpr int MAX_STACK = 96;  // DFS depth bound of the biWFA recursion
 constexpr int HIST_META_INTS = 16;
 constexpr int EDGE_ZONE = 64;  // I/D in-bounds tracking is only done this close to a wavefront end
 constexpr int SEQ_SMEM_WORDS = 2048;  // 8 KB of shared memory for the pair's packed sequences (guards included)
-// ---- shared-memory diagonal-band engine (phase 1 of the breakpoint search) ----
-constexpr int BAND_T = 32;            // scores advanced per band without leaving shared memory
-constexpr int BAND_WP = 1024;         // diagonals held per tile (output range + BAND_T halo either side)
-constexpr int BAND_WT = BAND_WP - 2 * BAND_T;
-constexpr int BAND_MROWS = 27;        // M history rows (max_score_scope <= 27)
-constexpr int BAND_ROWS = BAND_MROWS + 3 + 3 + 2 + 2 + 1;  // + I1, D1, I2, D2 windows + one all-NULL row
-constexpr int BAND_NULL_ROW = BAND_ROWS - 1;
-constexpr int BAND_TAB = 13;          // per-step table: RED_* layout
-constexpr int BAND_MIN_SCORE = 600;   // sub-problems expected to score less use the generic path
-constexpr short NULL16 = -16384;
-struct Meta16 {
-    int lo[5], hi[5], akM, akAll;
-};
-__host__ __device__ constexpr size_t band_smem_bytes(int scope) {
-    return sizeof(short) * BAND_ROWS * BAND_WP + sizeof(int) * 2 * (BAND_T + 1) * BAND_TAB + sizeof(Meta16) * 2 * (scope + BAND_T + 2) + 16;
-}
-
+// int16 wavefront storage: every negative value means "null".  Packed kernels let null values drift
+// upwards by +1 per insertion step, at most once per diagonal, so NULL16 + (plen + tlen) stays negative
+// (plan_launch only selects int16 when 2*tlen+plen and 2*plen+tlen are below 32000).
+constexpr short NULL16 = -32000;
+constexpr uint32_t NULL16X2 = 0x83008300u;
 enum { IN_MX = 0, IN_MO1, IN_I1E, IN_D1E, IN_MO2, IN_I2E, IN_D2E };
 enum { ST_OK = 0, ST_END_REACHED = 1, ST_FAIL_WORKSPACE = 2 };
 // red[] layout: per component c: RED_HI+c = max in-bounds k, RED_LO+c = max(-k); then the two
 // antidiagonal bounds and the value at the end cell
-enum { RED_HI = 0, RED_LO = 5, RED_AKM = 10, RED_AKALL = 11, RED_END = 12 };
+// int16 path only: RED_OOB = the row holds a non-null out-of-bounds cell, RED_CLO/RED_CHI = computed range of the row
+// (published by the planning warp), RED_FAIL = the row does not fit the workspace
+enum { RED_HI = 0, RED_LO = 5, RED_AKM = 10, RED_AKALL = 11, RED_END = 12, RED_OOB = 13, RED_CLO = 14, RED_CHI = 15, RED_FAIL = 16 };
 
 struct SlotMeta {
     int lo[5], hi[5];   // trimmed range per component; empty iff lo > hi
     int akM;            // max antidiagonal 2*off-k over valid extended M cells (INT_MIN if none)
     int akAll;          // upper bound of 2*off-k over every component's non-null cells
-    int clo, width;     // computed (allocated) range of this wavefront (history mode)
-    int off;            // workspace offset of the wavefront's component block (history mode)
+    int off;            // workspace element offset of (component 0, k = 0) of this wavefront
+    int cstride;        // elements between consecutive components
+    int wlo, whi;       // int16 rows: diagonals that read back correctly without masking (NULL outside the trimmed range)
 };
 
 struct In {
@@ -90,7 +85,6 @@ struct KParams {
     unsigned long long ws_ints_per_cta;
     int W;                   // allocated diagonals per ring wavefront
     int hist_ints;           // history arena size (ints)
-    long long ring16_int_off; // int offset inside the CTA workspace of the int16 band ring (2 x (scope+BAND_T+2) x ncomp x W halfwords), or -1
     int* ws_hist_meta;       // [cta][hist_max_scores][HIST_META_INTS]
     int hist_max_scores;
     uint32_t* ws_runs;       // [cta][2][runs_cap]: pair runs, then leaf scratch
@@ -124,6 +118,7 @@ __device__ __forceinline__ void red_max(int* red, int idx, int v) {
 // ---- K5: longest common prefix on packed words -------------------------------------------
 // BITS = 2 (2-bit packed, 16 symbols / word) or 8 (ASCII, 4 symbols / word).  Guard words
 // either side of every sequence make the over-reads legal; the result is clamped to maxlen.
+//@region lcp/extend helpers
 template <int BITS>
 __device__ __forceinline__ uint32_t load_fwd(const uint32_t* __restrict__ w, int pos) {
     constexpr int SPW = 32 / BITS;
@@ -226,6 +221,7 @@ __device__ __forceinline__ int to_ws<int>(int v) { return v; }
 template <>
 __device__ __forceinline__ short to_ws<short>(int v) { return (short)(v < 0 ? (int)NULL16 : v); }
 
+//@region wf_cells scalar
 struct StepOut {
     int lo[5], hi[5];
     int akM, akAll;
@@ -351,6 +347,280 @@ __device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7],
     red_max<NT>(red, RED_AKALL, akAll);
 }
 
+// ---- direction-generic match extension (one code path for the forward and the reverse aligner) ----
+// dir = +1 / rev = 0: symbols pos, pos+1, ... ; dir = -1 / rev = 1: symbols pos, pos-1, ...  In both cases the
+// returned word holds the first symbol to compare in its least significant bits.
+template <int BITS>
+__device__ __forceinline__ uint32_t load_dir(const uint32_t* __restrict__ w, int pos, int rev) {
+    constexpr int SPW = 32 / BITS;
+    const int idx = (int)((unsigned)pos / SPW) - rev;
+    const int sh = (int)(((unsigned)pos % SPW) + rev) * BITS;  // forward [0, 32-BITS], reverse [BITS, 32]
+    const uint32_t x = __funnelshift_rc(w[idx], w[idx + 1], sh);
+    return x;
+}
+// number of matching symbols (<= maxlen) from (v,h) in the aligner's direction; first = only one word
+template <int BITS>
+__device__ __forceinline__ int lcp_dir(const uint32_t* __restrict__ pw, const uint32_t* __restrict__ tw, int pp, int tp, int rev, int maxlen) {
+    constexpr int SPW = 32 / BITS;
+    const int dir = 1 - 2 * rev;
+    int n = 0;
+    while (n < maxlen) {
+        uint32_t x = load_dir<BITS>(pw, pp + dir * n, rev) ^ load_dir<BITS>(tw, tp + dir * n, rev);
+        if (x) {
+            if (rev) x = __brev(x);  // symbol pos sits in the most significant bits of a reverse word
+            n += (__ffs(x) - 1) / BITS;
+            break;
+        }
+        n += SPW;
+    }
+    return min(n, maxlen);
+}
+
+//@region wf_cells_v
+// ---- K4+K5, int16 storage: every thread owns CPT consecutive diagonals ("chunk") --------------
+// Rows are chunk-aligned in memory, so one 16-byte (CPT=8) or 8-byte (CPT=4) load fetches an input
+// row for the whole chunk; the recurrences run on packed int16x2 words (VIMNMX/VIADD.16x2), the
+// k-1 / k+1 neighbours come from the adjacent lanes by shuffle (lanes 0 and 31 of a warp are halo
+// lanes that only load), and only the match extension is scalar.
+//
+// Reads outside an input's trimmed [lo,hi] must see OFFSET_NULL (wavefront_compute_init_ends).
+// Every stored row therefore carries a NULL-filled margin of VMARGIN diagonals either side of its
+// computed range, and its SlotMeta says which diagonals [wlo,whi] read back correctly without
+// masking; absent inputs point at an all-NULL row.  A chunk inside every input's [wlo,whi] takes
+// plain vector loads, the rest mask element by element.
+//
+// wavefront_compute_trim_ends without per-cell tracking: as long as no cell of the row is a
+// non-null offset outside the sequences ("oob"; M's pre-null value dominates every component at
+// its diagonal, so testing that one value covers all five), the trimmed range of every output
+// component follows arithmetically from the inputs' trimmed ranges (their end cells are in bounds,
+// hence non-null).  Rows that do hold such a cell raise RED_OOB and are trimmed exactly by
+// wf_rescan after the barrier.
+constexpr int VMARGIN = 48;
+constexpr int VBIG = 1 << 28;
+
+template <int CPT>
+__device__ __forceinline__ void ld_vec(const short* __restrict__ p, uint32_t (&v)[CPT / 2]) {
+    if constexpr (CPT == 8) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else if constexpr (CPT == 4) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+        v[0] = *reinterpret_cast<const uint32_t*>(p);
+    }
+}
+template <int CPT>
+__device__ __forceinline__ void st_vec(short* __restrict__ p, const uint32_t (&v)[CPT / 2]) {
+    if constexpr (CPT == 8) {
+        *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (CPT == 4) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]);
+    } else {
+        *reinterpret_cast<uint32_t*>(p) = v[0];
+    }
+}
+// input row at diagonals [kc, kc+CPT): NULL outside the row's trimmed range [lo,hi]
+template <int CPT>
+__device__ __forceinline__ void load_row(const short* __restrict__ ws, int off, int lo, int hi, int kc, uint32_t (&v)[CPT / 2]) {
+    constexpr int VW = CPT / 2;
+    const int k1 = kc + CPT - 1;
+    if (k1 < lo || kc > hi) {
+#pragma unroll
+        for (int i = 0; i < VW; ++i) v[i] = NULL16X2;
+        return;
+    }
+    ld_vec<CPT>(ws + off + kc, v);
+    if (kc < lo || k1 > hi) {
+#pragma unroll
+        for (int i = 0; i < VW; ++i) {
+            const int k = kc + 2 * i;
+            const bool a = (k >= lo && k <= hi), b = (k + 1 >= lo && k + 1 <= hi);
+            v[i] = (a ? (v[i] & 0xffffu) : (NULL16X2 & 0xffffu)) | (b ? (v[i] & 0xffff0000u) : (NULL16X2 & 0xffff0000u));
+        }
+    }
+}
+__device__ __forceinline__ int half_lo(uint32_t w) { return (int)(short)(w & 0xffffu); }
+__device__ __forceinline__ int half_hi(uint32_t w) { return (int)w >> 16; }
+
+// Called by the `gnw` warps of a group (gwarp = this warp's index in the group).
+//   in_off  : lane i < 7 holds the element offset (k = 0) of input i (IN_*); the NULL row when absent
+//   dsc     : warp-private shared memory, dsc[i] / dsc[8+i] = trimmed lo / hi of input i (empty: lo > hi)
+//   out_off : element offset (k = 0) of output component 0, components are `cstride` apart
+//   [lo,hi] : computed range; [fast_lo,fast_hi] : diagonals every input reads back unmasked
+//   [wlo,whi]: what this row must leave readable (computed chunks + NULL margin, clipped to the allocation)
+template <int BITS, bool TWO, int CPT>
+__device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, const int* dsc, int out_off, int cstride, int lo, int hi, int fast_lo, int fast_hi,
+                                        int wlo, int whi, const uint32_t* __restrict__ s_pw, const uint32_t* __restrict__ s_tw, int s_p0, int s_t0, int s_plen,
+                                        int s_tlen, int rev, int k_end, int comp_end, int* red, int gwarp, int gnw) {
+    constexpr int VW = CPT / 2;
+    constexpr int SH = (CPT == 8) ? 3 : (CPT == 4 ? 2 : 1);
+    constexpr int OWN = 30;  // chunks owned per warp iteration (lanes 1..30)
+    const int lane = threadIdx.x & 31;
+    constexpr int SPW = 32 / BITS;
+    const unsigned tlen = (unsigned)s_tlen, plen = (unsigned)s_plen;
+    const int dir = 1 - 2 * rev;
+    const int o_mx = __shfl_sync(0xffffffffu, in_off, IN_MX), o_mo1 = __shfl_sync(0xffffffffu, in_off, IN_MO1);
+    const int o_i1e = __shfl_sync(0xffffffffu, in_off, IN_I1E), o_d1e = __shfl_sync(0xffffffffu, in_off, IN_D1E);
+    int o_mo2 = 0, o_i2e = 0, o_d2e = 0;
+    if (TWO) {
+        o_mo2 = __shfl_sync(0xffffffffu, in_off, IN_MO2);
+        o_i2e = __shfl_sync(0xffffffffu, in_off, IN_I2E);
+        o_d2e = __shfl_sync(0xffffffffu, in_off, IN_D2E);
+    }
+    const int c_lo = lo >> SH, c_hi = hi >> SH;  // arithmetic shift = floor
+    const int o_m = out_off, o_i1 = out_off + cstride, o_i2 = out_off + 2 * cstride, o_d1 = out_off + (TWO ? 3 : 2) * cstride, o_d2 = out_off + 4 * cstride;
+    int akM = INT_MIN, akAll = INT_MIN;
+    bool oob = false;
+    for (int cw = c_lo + gwarp * OWN; cw <= c_hi; cw += gnw * OWN) {
+        const int c = cw - 1 + lane;
+        const int kc = c << SH;
+        const bool own = (lane >= 1) && (lane <= OWN) && (c <= c_hi);
+        const bool fast = (kc >= fast_lo) && (kc + CPT - 1 <= fast_hi);
+        uint32_t mx[VW], tI1[VW], tD1[VW], tI2[VW], tD2[VW];
+        {
+            uint32_t mo[VW], ie[VW], de[VW], mo2[VW], ie2[VW], de2[VW];
+            if (fast) {
+                const short* pk = ws + kc;
+                ld_vec<CPT>(pk + o_mx, mx);
+                ld_vec<CPT>(pk + o_mo1, mo);
+                ld_vec<CPT>(pk + o_i1e, ie);
+                ld_vec<CPT>(pk + o_d1e, de);
+                if (TWO) {
+                    ld_vec<CPT>(pk + o_mo2, mo2);
+                    ld_vec<CPT>(pk + o_i2e, ie2);
+                    ld_vec<CPT>(pk + o_d2e, de2);
+                }
+            } else {
+                load_row<CPT>(ws, o_mx, dsc[IN_MX], dsc[8 + IN_MX], kc, mx);
+                load_row<CPT>(ws, o_mo1, dsc[IN_MO1], dsc[8 + IN_MO1], kc, mo);
+                load_row<CPT>(ws, o_i1e, dsc[IN_I1E], dsc[8 + IN_I1E], kc, ie);
+                load_row<CPT>(ws, o_d1e, dsc[IN_D1E], dsc[8 + IN_D1E], kc, de);
+                if (TWO) {
+                    load_row<CPT>(ws, o_mo2, dsc[IN_MO2], dsc[8 + IN_MO2], kc, mo2);
+                    load_row<CPT>(ws, o_i2e, dsc[IN_I2E], dsc[8 + IN_I2E], kc, ie2);
+                    load_row<CPT>(ws, o_d2e, dsc[IN_D2E], dsc[8 + IN_D2E], kc, de2);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < VW; ++i) {
+                tI1[i] = __vmaxs2(mo[i], ie[i]);
+                tD1[i] = __vmaxs2(mo[i], de[i]);
+                if (TWO) {
+                    tI2[i] = __vmaxs2(mo2[i], ie2[i]);
+                    tD2[i] = __vmaxs2(mo2[i], de2[i]);
+                }
+            }
+        }
+        // neighbours: element kc-1 of the insertion sources, element kc+CPT of the deletion sources
+        const uint32_t pI1 = __shfl_up_sync(0xffffffffu, tI1[VW - 1], 1);
+        const uint32_t nD1 = __shfl_down_sync(0xffffffffu, tD1[0], 1);
+        uint32_t pI2 = 0, nD2 = 0;
+        if (TWO) {
+            pI2 = __shfl_up_sync(0xffffffffu, tI2[VW - 1], 1);
+            nD2 = __shfl_down_sync(0xffffffffu, tD2[0], 1);
+        }
+        if (own) {
+            uint32_t vI1[VW], vD1[VW], vI2[VW], vD2[VW], vM[VW];
+#pragma unroll
+            for (int i = 0; i < VW; ++i) {
+                vI1[i] = __byte_perm(i == 0 ? pI1 : tI1[i - 1], tI1[i], 0x5432) + 0x00010001u;  // nulls never hold 0xffff: no carry between halves
+                vD1[i] = __byte_perm(tD1[i], i == VW - 1 ? nD1 : tD1[i + 1], 0x5432);
+                uint32_t m = __viaddmax_s16x2(mx[i], 0x00010001u, vI1[i]);
+                if (TWO) {
+                    vI2[i] = __byte_perm(i == 0 ? pI2 : tI2[i - 1], tI2[i], 0x5432) + 0x00010001u;
+                    vD2[i] = __byte_perm(tD2[i], i == VW - 1 ? nD2 : tD2[i + 1], 0x5432);
+                    m = __vimax3_s16x2(m, vI2[i], vD1[i]);
+                    m = __vmaxs2(m, vD2[i]);
+                } else {
+                    m = __vmaxs2(m, vD1[i]);
+                }
+                vM[i] = m;
+            }
+            short* pk = ws + kc;
+            st_vec<CPT>(pk + o_i1, vI1);
+            st_vec<CPT>(pk + o_d1, vD1);
+            if (TWO) {
+                st_vec<CPT>(pk + o_i2, vI2);
+                st_vec<CPT>(pk + o_d2, vD2);
+            }
+            if (comp_end != AW_COMP_M && k_end >= kc && k_end < kc + CPT) {
+                const int j = k_end - kc;
+                const uint32_t* src = (comp_end == AW_COMP_I1) ? vI1 : (comp_end == AW_COMP_D1) ? vD1 : (comp_end == AW_COMP_I2) ? vI2 : vD2;
+                uint32_t wsel = src[0];
+#pragma unroll
+                for (int i = 1; i < VW; ++i)
+                    if ((j >> 1) == i) wsel = src[i];
+                red[RED_END] = (j & 1) ? half_hi(wsel) : half_lo(wsel);
+            }
+            int mm[CPT], nn[CPT];
+            unsigned more = 0;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const int k = kc + j;
+                const int m = (j & 1) ? half_hi(vM[j >> 1]) : half_lo(vM[j >> 1]);
+                const bool valid = !((unsigned)m > tlen || (unsigned)(m - k) > plen);
+                if (m >= 0) {
+                    akAll = max(akAll, 2 * m - k);  // m (pre-null) dominates every component at k
+                    oob = oob || !valid;
+                }
+                mm[j] = valid ? m : -1;
+                // first round of the extension (one word), branch-free; invalid cells compare position 0
+                const int maxlen = valid ? min(s_plen - (m - k), s_tlen - m) : 0;
+                const int v = (maxlen > 0) ? m - k : 0, h = (maxlen > 0) ? m : 0;  // nothing to compare: keep the (unused) loads inside the sequences
+                uint32_t x = load_dir<BITS>(s_pw, s_p0 + dir * v, rev) ^ load_dir<BITS>(s_tw, s_t0 + dir * h, rev);
+                if (rev) x = __brev(x);
+                const int cnt = x ? (__ffs(x) - 1) / BITS : SPW;
+                nn[j] = min(cnt, maxlen);
+                if (x == 0 && maxlen > SPW) more |= 1u << j;
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) mm[j] += nn[j];
+            if (more) {  // long match runs: continue word by word
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    if (more & (1u << j)) {
+                        const int v = mm[j] - (kc + j), h = mm[j];
+                        mm[j] += lcp_dir<BITS>(s_pw, s_tw, s_p0 + dir * v, s_t0 + dir * h, rev, min(s_plen - v, s_tlen - h));
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                if (mm[j] >= 0) akM = max(akM, 2 * mm[j] - (kc + j));
+                else mm[j] = NULL16;
+                if (comp_end == AW_COMP_M && kc + j == k_end) red[RED_END] = mm[j];
+            }
+#pragma unroll
+            for (int i = 0; i < VW; ++i) vM[i] = __byte_perm((uint32_t)mm[2 * i], (uint32_t)mm[2 * i + 1], 0x5410);
+            st_vec<CPT>(pk + o_m, vM);
+        }
+    }
+    // NULL margin either side of the computed chunks (clipped to [wlo,whi]), by the group's last warp
+    if (gwarp == gnw - 1) {
+        constexpr int MG = VMARGIN / CPT;
+        constexpr int NCOMP = TWO ? 5 : 3;
+        uint32_t nullv[VW];
+#pragma unroll
+        for (int i = 0; i < VW; ++i) nullv[i] = NULL16X2;
+        for (int i = lane; i < 2 * MG * NCOMP; i += 32) {
+            const int comp = i / (2 * MG), j = i - comp * (2 * MG);
+            const int c = (j < MG) ? (c_lo - MG + j) : (c_hi + 1 + (j - MG));
+            const int kc = c << SH;
+            if (kc >= wlo && kc + CPT - 1 <= whi) st_vec<CPT>(ws + out_off + comp * cstride + kc, nullv);
+        }
+    }
+    akM = __reduce_max_sync(0xffffffffu, akM);
+    akAll = __reduce_max_sync(0xffffffffu, akAll);
+    oob = __any_sync(0xffffffffu, oob);
+    if (lane == 0) {
+        if (akM != INT_MIN) atomicMax(&red[RED_AKM], akM);
+        if (akAll != INT_MIN) atomicMax(&red[RED_AKALL], akAll);
+        if (oob) red[RED_OOB] = 1;
+    }
+}
+
+//@region wf_finish
 // after the barrier: trimmed ranges (wavefront_compute_trim_ends) from the reductions
 template <bool TWO>
 __device__ __forceinline__ void wf_finish(const int* red, int lo, int hi, StepOut& so) {
@@ -380,6 +650,7 @@ __device__ __forceinline__ void wf_finish(const int* red, int lo, int hi, StepOu
     so.endval = red[RED_END];
 }
 
+//@region wf_rescan
 // exact trim of every component by re-reading the stored wavefront (rare slow path)
 template <int NT, bool TWO, class WS>
 __device__ __noinline__ void wf_rescan(const WS* __restrict__ ws, const int (&out)[5], int lo, int hi, int plen_, int tlen_, int* red, StepOut& so) {
@@ -426,6 +697,7 @@ __device__ __noinline__ void wf_rescan(const WS* __restrict__ ws, const int (&ou
     cta_sync<NT>();
 }
 
+//@region misc helpers
 __device__ __forceinline__ bool end_reached(const StepOut& so, int comp_end, int k_end, int tlen) {
     const int l = (comp_end == AW_COMP_M) ? so.lo[0] : (comp_end == AW_COMP_I1) ? so.lo[1] : (comp_end == AW_COMP_I2) ? so.lo[2] : (comp_end == AW_COMP_D1) ? so.lo[3] : so.lo[4];
     const int h = (comp_end == AW_COMP_M) ? so.hi[0] : (comp_end == AW_COMP_I1) ? so.hi[1] : (comp_end == AW_COMP_I2) ? so.hi[2] : (comp_end == AW_COMP_D1) ? so.hi[3] : so.hi[4];
@@ -488,9 +760,13 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
+//@region kernel prologue + pair setup
 template <int NT, int BITS, bool TWO, class WS>
-__global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 128 ? 4 : 1)) aw_align_kernel(const KParams P) {
+__global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const KParams P) {
     constexpr int NCOMP = TWO ? 5 : 3;
+    constexpr bool VEC = (sizeof(WS) == 2) && (NT >= 64);  // chunk-vectorised int16 cell loop
+    constexpr int CPT = AW_CPT;                            // diagonals per thread in that loop
+    constexpr int RALIGN = VEC ? 8 : 1;                    // row alignment (elements)
     extern __shared__ unsigned long long smem_raw[];
     const int scope = P.pen.scope;
     const int ring_n = scope + 1;  // one spare slot: the reverse step is computed speculatively
@@ -498,15 +774,6 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
     int* cand = reinterpret_cast<int*>(ring_meta + 2 * ring_n);                                     // [scope*5] candidate tests
     int* hitk = cand + scope * 5;                                                                    // [scope*5] first hit per candidate
     unsigned long long* scanbuf = reinterpret_cast<unsigned long long*>(hitk + scope * 5);  // [NT]; 8-byte aligned: 60*2*ring_n + 40*scope
-#ifndef AW_ENABLE_BAND
-#define AW_ENABLE_BAND 0  // the shared-memory diagonal-band engine is experimental: measured slower than the generic loop
-#endif
-    constexpr bool BAND = (NT == 256) && (AW_ENABLE_BAND != 0);
-    const int rn16 = scope + BAND_T + 2;  // slots of the int16 band ring
-    short* band_rows = reinterpret_cast<short*>(scanbuf + NT);                    // [BAND_ROWS][BAND_WP]
-    int* band_tab = reinterpret_cast<int*>(band_rows + BAND_ROWS * BAND_WP);      // [2][BAND_T+1][BAND_TAB]
-    Meta16* meta16 = reinterpret_cast<Meta16*>(band_tab + 2 * (BAND_T + 1) * BAND_TAB);  // [2][rn16]
-    __shared__ int s_band_flag;
     __shared__ int red[2][3][NRED];
     __shared__ SubProblem stack[MAX_STACK];
     __shared__ unsigned s_next;
@@ -515,18 +782,24 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
     __shared__ unsigned long long s_acc[8];
     __shared__ unsigned long long s_text_off, s_bytes_off;
     __shared__ uint32_t s_seq[SEQ_SMEM_WORDS];
+    __shared__ __align__(16) int s_desc[VEC ? NT / 32 : 1][16];  // int16 path: per-warp trimmed lo[8] / hi[8] of the step's inputs
 
     const int tid = threadIdx.x;
     const AwPen pen = P.pen;
     int* const ws_i = P.ws + (size_t)blockIdx.x * P.ws_ints_per_cta;
     WS* const ws = reinterpret_cast<WS*>(ws_i);  // all wavefront offsets below are in WS elements
     const int W = P.W;
-    const int hist_base = 2 * ring_n * NCOMP * W;  // history arena starts after the rings
+    const int null_base = 2 * ring_n * NCOMP * W;               // int16 path: one all-NULL row after the rings
+    const int hist_base = null_base + (VEC ? W : 0);            // history arena starts after the rings
     int* const hist_meta = P.ws_hist_meta + (size_t)blockIdx.x * (size_t)P.hist_max_scores * HIST_META_INTS;
     uint32_t* const pair_runs = P.ws_runs + (size_t)blockIdx.x * 2 * P.runs_cap;
     uint32_t* const leaf_runs = pair_runs + P.runs_cap;
 
-    if (tid < 2 * 3 * NRED) (&red[0][0][0])[tid] = INT_MIN;
+    for (int i = tid; i < 2 * 3 * NRED; i += NT) (&red[0][0][0])[i] = INT_MIN;
+    if constexpr (VEC) {
+        const uint4 nv = make_uint4(NULL16X2, NULL16X2, NULL16X2, NULL16X2);
+        for (int i = tid * 8; i < W; i += NT * 8) *reinterpret_cast<uint4*>(ws + null_base + i) = nv;
+    }
     int red_i = 0;  // rotating reduction buffer index (uniform)
     cta_sync<NT>();
 
@@ -566,7 +839,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                 tw = s_seq + pwords + 4 + 2;
             }
         }
-        const int koff = min(PLEN + 1, W / 2);  // diagonal k lives at index k + koff
+        const int koff = (min(PLEN + 1, W / 2) + RALIGN - 1) & ~(RALIGN - 1);  // diagonal k lives at index k + koff
         const int kmin_alloc = -koff, kmax_alloc = W - 1 - koff;
 
         int status = ST_OK;
@@ -606,9 +879,10 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                 m.hi[c] = 0;
             }
             m.akM = m.akAll = INT_MIN;
-            m.clo = 0;
-            m.width = 0;
             m.off = 0;
+            m.cstride = 0;
+            m.wlo = 1;
+            m.whi = 0;
         };
         auto store_meta = [&](SlotMeta& m, const StepOut& so) {
 #pragma unroll
@@ -640,6 +914,234 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
             }
         };
 
+//@region v_launch (plan + cells)
+        // ================= int16 path: one wavefront step =================
+        // v_launch: the warps of a group plan wavefront `s` of direction d (inputs, ranges, placement) and
+        // compute it; nothing here needs a barrier.  v_finish (every thread, after the barrier) publishes
+        // the step's results.  mbase selects the SlotMeta ring (d * ring_n; 0 in the base case).
+        struct VRange {
+            int lo, hi;   // computed range (null step iff lo > hi); valid in the planning warps only
+            int width;    // history mode: allocated elements per component
+        };
+        long long hist_used = 0;  // history arena bump pointer (base case)
+        auto v_launch = [&](int d, int mbase, int s, int slot, int gwarp, int gnw, bool hist, const SeqView& sv, int k_end, int comp_end) -> VRange {
+            constexpr int SH = (CPT == 8) ? 3 : (CPT == 4 ? 2 : 1);
+            constexpr int MG = VMARGIN / CPT;
+            const int lane = tid & 31;
+            int* r = red[d][red_i];
+            int* dsc = s_desc[VEC ? (tid >> 5) : 0];
+            SlotMeta& mt = ring_meta[mbase + slot];
+            // lane i < 7 describes input i
+            int comp = AW_COMP_M, back = pen.x;
+            if (lane == IN_MO1) back = pen.o1 + pen.e1;
+            else if (lane == IN_I1E) { comp = AW_COMP_I1; back = pen.e1; }
+            else if (lane == IN_D1E) { comp = AW_COMP_D1; back = pen.e1; }
+            else if (lane == IN_MO2) back = pen.o2 + pen.e2;
+            else if (lane == IN_I2E) { comp = AW_COMP_I2; back = pen.e2; }
+            else if (lane == IN_D2E) { comp = AW_COMP_D2; back = pen.e2; }
+            int ilo = VBIG, ihi = -VBIG, ioff = null_base + koff, iwlo = -VBIG, iwhi = VBIG;
+            if (lane < (TWO ? 7 : 4) && s - back >= 0) {
+                int sl = slot - back;
+                if (sl < 0) sl += ring_n;
+                const SlotMeta& m = ring_meta[mbase + sl];
+                const int l = m.lo[comp], h = m.hi[comp];
+                if (l <= h) {
+                    ilo = l;
+                    ihi = h;
+                    ioff = m.off + comp_idx(comp) * m.cstride;
+                    iwlo = m.wlo;
+                    iwhi = m.whi;
+                }
+            }
+            __syncwarp();
+            if (lane < 8) {
+                dsc[lane] = ilo;
+                dsc[8 + lane] = ihi;
+            }
+            const int fast_lo = max(__reduce_max_sync(0xffffffffu, iwlo), kmin_alloc);
+            const int fast_hi = min(__reduce_min_sync(0xffffffffu, iwhi), kmax_alloc);
+            __syncwarp();
+            const int4 l0 = *reinterpret_cast<const int4*>(dsc), l1 = *reinterpret_cast<const int4*>(dsc + 4);
+            const int4 h0 = *reinterpret_cast<const int4*>(dsc + 8), h1 = *reinterpret_cast<const int4*>(dsc + 12);
+            // trimmed ranges of the outputs when the row holds no out-of-bounds cell (see wf_cells_v)
+            const int i1lo = min(l0.y, l0.z) + 1, i1hi = max(h0.y, h0.z) + 1;
+            const int d1lo = min(l0.y, l0.w) - 1, d1hi = max(h0.y, h0.w) - 1;
+            const int i2lo = min(l1.x, l1.y) + 1, i2hi = max(h1.x, h1.y) + 1;
+            const int d2lo = min(l1.x, l1.z) - 1, d2hi = max(h1.x, h1.z) - 1;
+            const int mlo = min(min(l0.x, min(i1lo, i2lo)), min(d1lo, d2lo)), mhi = max(max(h0.x, max(i1hi, i2hi)), max(d1hi, d2hi));
+            VRange rg;
+            rg.lo = mlo;  // = wavefront_compute_limits_input over the non-empty inputs
+            rg.hi = mhi;
+            rg.width = 0;
+            const bool lead = (gwarp == 0);
+            if (status != ST_OK) return rg;
+            if (rg.lo > rg.hi) {  // null step
+                if (lead) {
+                    if (lane < 5) {
+                        mt.lo[lane] = 1;
+                        mt.hi[lane] = 0;
+                    }
+                    if (lane == 5) {
+                        mt.akM = mt.akAll = INT_MIN;
+                        mt.off = mt.cstride = 0;
+                        mt.wlo = 1;
+                        mt.whi = 0;
+                        r[RED_CLO] = 1;
+                        r[RED_CHI] = 0;
+                    }
+                }
+                return rg;
+            }
+            const int c_lo = rg.lo >> SH, c_hi = rg.hi >> SH;
+            int out_off, cstride, wlo, whi;
+            bool fail = false;
+            if (!hist) {
+                fail = (rg.lo < kmin_alloc || rg.hi > kmax_alloc);
+                out_off = ((d * ring_n + slot) * NCOMP) * W + koff;
+                cstride = W;
+                wlo = max((c_lo - MG) << SH, kmin_alloc);
+                whi = min(((c_hi + MG + 1) << SH) - 1, kmax_alloc);
+            } else {
+                const int clo = (c_lo - MG) << SH;
+                rg.width = (c_hi - c_lo + 1 + 2 * MG) << SH;
+                fail = (hist_used + (long long)NCOMP * rg.width > (long long)P.hist_ints);
+                out_off = hist_base + (int)hist_used - clo;
+                cstride = rg.width;
+                wlo = clo;
+                whi = clo + rg.width - 1;
+            }
+            if (fail) {
+                if (lead && lane == 0) r[RED_FAIL] = 1;
+                return rg;
+            }
+            if (lead) {
+                if (lane < 5) {
+                    int pl = (lane == AW_COMP_M) ? mlo : (lane == AW_COMP_I1) ? i1lo : (lane == AW_COMP_I2) ? i2lo : (lane == AW_COMP_D1) ? d1lo : d2lo;
+                    int ph = (lane == AW_COMP_M) ? mhi : (lane == AW_COMP_I1) ? i1hi : (lane == AW_COMP_I2) ? i2hi : (lane == AW_COMP_D1) ? d1hi : d2hi;
+                    if (pl > ph) {
+                        pl = 1;
+                        ph = 0;
+                    }
+                    mt.lo[lane] = pl;
+                    mt.hi[lane] = ph;
+                }
+                if (lane == 5) {
+                    mt.off = out_off;
+                    mt.cstride = cstride;
+                    mt.wlo = wlo;
+                    mt.whi = whi;
+                    r[RED_CLO] = rg.lo;
+                    r[RED_CHI] = rg.hi;
+                }
+            }
+            if constexpr (VEC)
+                wf_cells_v<BITS, TWO, CPT>(reinterpret_cast<short*>(ws), ioff, dsc, out_off, cstride, rg.lo, rg.hi, fast_lo, fast_hi, wlo, whi, sv.pw, sv.tw, sv.p0, sv.t0,
+                                           sv.plen, sv.tlen, sv.rev ? 1 : 0, k_end, comp_end, r, gwarp, gnw);
+            return rg;
+        };
+//@region v_finish
+        // after the barrier: END_REACHED of the new wavefront; akM_out = its max M antidiagonal
+        auto v_finish = [&](int d, int mbase, int slot, int plen, int tlen, int k_end, int comp_end, int& akM_out) -> bool {
+            int* r = red[d][red_i];
+            const int clo = r[RED_CLO], chi = r[RED_CHI], akM = r[RED_AKM], akAll = r[RED_AKALL], endval = r[RED_END];
+            const bool fail = r[RED_FAIL] != INT_MIN, oob = r[RED_OOB] != INT_MIN;
+            akM_out = INT_MIN;
+            ++w_steps;
+            if (status != ST_OK) return false;
+            if (fail) {
+                status = ST_FAIL_WORKSPACE;
+                return false;
+            }
+            if (clo > chi) return false;
+            w_cells += (unsigned long long)(chi - clo + 1) * NCOMP;
+            SlotMeta& mt = ring_meta[mbase + slot];
+            if (oob) {  // exact wavefront_compute_trim_ends from the stored row (rare)
+                int out[5];
+                const int off = mt.off, cs = mt.cstride;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) out[c] = off + comp_idx((TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M) * cs;
+                StepOut so;
+                wf_rescan<NT, TWO, WS>(ws, out, clo, chi, plen, tlen, r, so);
+                if (tid < 32) {
+                    int wl = -VBIG, wh = VBIG;  // cells outside a component's trimmed range hold garbage: only the common part reads unmasked
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) {
+                        mt.lo[c] = so.lo[c];
+                        mt.hi[c] = so.hi[c];
+                        if (so.lo[c] <= so.hi[c]) {
+                            wl = max(wl, so.lo[c]);
+                            wh = min(wh, so.hi[c]);
+                        }
+                    }
+                    mt.wlo = wl;
+                    mt.whi = wh;
+                }
+                cta_sync<NT>();
+            }
+            if (tid < 32) {
+                mt.akM = akM;
+                mt.akAll = akAll;
+            }
+            akM_out = akM;
+            return mt.lo[comp_end] <= k_end && k_end <= mt.hi[comp_end] && endval >= tlen;
+        };
+        // score-0 wavefront (wavefront_unialign_init_end2end): cell 0 of component `cb` inside a NULL-filled neighbourhood
+        auto v_init_row = [&](int d, int mbase, bool hist, const SeqView& sv, int cb, int ce, int k_end, int& akM_out) -> bool {
+            constexpr int SH = (CPT == 8) ? 3 : (CPT == 4 ? 2 : 1);
+            constexpr int MG = VMARGIN / CPT;
+            int* r = red[d][red_i];
+            SlotMeta& mt = ring_meta[mbase];
+            int out_off, cstride;
+            const int clo = max((-MG) << SH, kmin_alloc), chi = min(((MG + 1) << SH) - 1, kmax_alloc);
+            if (!hist) {
+                out_off = ((d * ring_n) * NCOMP) * W + koff;
+                cstride = W;
+            } else {
+                cstride = chi - clo + 1;
+                out_off = hist_base - clo;
+                hist_used = (long long)NCOMP * cstride;
+            }
+            if constexpr (VEC) {
+                short* row = reinterpret_cast<short*>(ws) + out_off + comp_idx(cb) * cstride;
+                if (tid <= 2 * MG) {
+                    const int kc = (tid - MG) << SH;
+                    uint32_t v[CPT / 2];
+#pragma unroll
+                    for (int i = 0; i < CPT / 2; ++i) v[i] = NULL16X2;
+                    if (kc == 0) {
+                        int m = 0;
+                        if (cb == AW_COMP_M) m = extend_cell<BITS>(sv, 0, 0);
+                        v[0] = (v[0] & 0xffff0000u) | ((uint32_t)m & 0xffffu);
+                        r[RED_AKM] = (cb == AW_COMP_M) ? 2 * m : INT_MIN;
+                        r[RED_AKALL] = 2 * m;
+                        if (cb == ce && k_end == 0) r[RED_END] = m;
+                    }
+                    if (kc >= clo && kc + CPT - 1 <= chi) st_vec<CPT>(row + kc, v);
+                }
+            }
+            if (tid < 32) {
+                if (tid < 5) {
+                    mt.lo[tid] = (tid == cb) ? 0 : 1;
+                    mt.hi[tid] = 0;
+                }
+                if (tid == 5) {
+                    mt.off = out_off;
+                    mt.cstride = cstride;
+                    mt.wlo = clo;
+                    mt.whi = chi;
+                }
+            }
+            cta_sync<NT>();
+            const int akM = r[RED_AKM], endval = r[RED_END];
+            if (tid < 32) {
+                mt.akM = akM;
+                mt.akAll = r[RED_AKALL];
+            }
+            akM_out = akM;
+            return k_end == 0 && endval >= sv.tlen;  // only component cb is non-empty, at k = 0
+        };
+
+//@region subproblem setup
         while (sp_n > 0 && status == ST_OK) {
             const SubProblem sp = stack[--sp_n];
             const int plen = sp.pe - sp.pb, tlen = sp.te - sp.tb;
@@ -705,6 +1207,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                     for (int c = 0; c < 5; ++c) out[c] = ring_off(d, slot, (TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M);
                 };
                 // descriptors + limits + cell loop of wavefront `s` (ring slot `slot`) of direction d; no barrier
+//@region launch_dir
                 auto launch_dir = [&](int d, int s, int slot) -> Range {
                     In in[7];
                     auto fetch = [&](int c, int back) -> In {
@@ -751,6 +1254,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                     return r;
                 };
                 // after the barrier: trimmed ranges -> ring meta; returns END_REACHED of this wavefront
+//@region finish_dir
                 auto finish_dir = [&](int d, int slot, const Range& r) -> bool {
                     SlotMeta& mt = ring_meta[d * ring_n + slot];
                     if (r.lo > r.hi || status != ST_OK) {
@@ -769,6 +1273,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                 };
                 auto next_slot = [&](int slot) -> int { return slot + 1 == ring_n ? 0 : slot + 1; };
 
+//@region overlap
                 // wavefront_bialign_overlap: A0 = direction d0 at score s0, A1 = direction d1 at scores s1..s1-scope+1
                 auto overlap = [&](int d0, int d1, int s0, int s1) {
                     const int slot0 = cur_slot[d0];
@@ -872,395 +1377,59 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                     cta_sync<NT>();  // cand/hitk are rewritten by the next call
                 };
 
+//@region phase driver
                 StepOut so;
                 int score_f = 0, score_r = 0, f_ak = 0, r_ak = 0;
                 bool fb_end = false;  // END_REACHED -> fall back to the base case
-                init_dir(0, so);
-                if (end_reached(so, cend[0], k_end, tlen)) fb_end = true;
-                f_ak = max(0, so.akM);
-                if (!fb_end) {
-                    init_dir(1, so);
-                    if (end_reached(so, cend[1], k_end, tlen)) fb_end = true;
-                    r_ak = max(0, so.akM);
+                if constexpr (VEC) {
+                    int ak;
+                    if (v_init_row(0, 0, false, svd[0], cbeg[0], cend[0], k_end, ak)) fb_end = true;
+                    rotate_red();
+                    f_ak = max(0, ak);
+                    if (!fb_end) {
+                        if (v_init_row(1, ring_n, false, svd[1], cbeg[1], cend[1], k_end, ak)) fb_end = true;
+                        rotate_red();
+                        r_ak = max(0, ak);
+                    }
+                } else {
+                    init_dir(0, so);
+                    if (end_reached(so, cend[0], k_end, tlen)) fb_end = true;
+                    f_ak = max(0, so.akM);
+                    if (!fb_end) {
+                        init_dir(1, so);
+                        if (end_reached(so, cend[1], k_end, tlen)) fb_end = true;
+                        r_ak = max(0, so.akM);
+                    }
                 }
                 bool last_forward = false;
                 bool rev_pending = false;  // reverse wavefront score_r+1 already sits in slot next_slot(cur_slot[1])
                 const int max_antidiagonal = plen + tlen - 1;
                 bool rev_pending_done = false;  // END_REACHED flag of that speculative wavefront
                 lap(4);
-                // =========== shared-memory diagonal-band engine for phase 1 ===========
-                // Advances both directions BAND_T scores at a time inside shared memory (int16 offsets,
-                // NULL-filled halos, no range checks, one barrier per step), streams every produced row to
-                // an int16 ring in global memory, then replays WFA2's alternation over the per-step table
-                // to find the exact break.  Anything it cannot resolve locally (an out-of-bounds positive
-                // I/D offset, whose trimming depends on the whole row) aborts the band: the generic loop
-                // below then redoes phase 1 from score 0.  Hand-over converts the last `scope` rows to the
-                // generic int32 ring so that phase 2 (overlap) runs on the proven path.
-                bool band_done = false;
-                if constexpr (BAND)
-                if (!fb_end && P.ring16_int_off >= 0 && scope <= BAND_MROWS && pen.e1 <= 2 && (!TWO || pen.e2 <= 1) && sp.rem > BAND_MIN_SCORE &&
-                    2 * tlen + plen < 32000 && 2 * plen + tlen < 32000) {
-                    short* const ring16 = reinterpret_cast<short*>(ws_i + P.ring16_int_off);
-                    auto r16_off = [&](int d, int slot, int c) -> long long { return ((long long)((d * rn16 + slot) * NCOMP + comp_idx(c))) * W + koff; };
-                    // row 0 of both directions (written by init_dir) -> int16 ring + meta
-                    if (tid < 2) {
-                        const int d = tid;
-                        ring16[r16_off(d, 0, cbeg[d])] = (short)ws[ring_off(d, 0, cbeg[d])];
-                    }
-                    for (int d = 0; d < 2; ++d) {
-                        const SlotMeta& m = ring_meta[d * ring_n + 0];
-                        Meta16& q = meta16[d * rn16 + 0];
-#pragma unroll
-                        for (int c = 0; c < 5; ++c) {
-                            q.lo[c] = m.lo[c];
-                            q.hi[c] = m.hi[c];
-                        }
-                        q.akM = m.akM;
-                        q.akAll = m.akAll;
-                    }
-                    if (tid == 0) s_band_flag = 0;
-                    cta_sync<NT>();
-                    int S = 0;        // both directions are complete up to score S
-                    int slotS = 0;    // int16 ring slot of score S
-                    bool band_fail = false, band_break = false;
-                    // smem row of a score (negative score -> the all-NULL row)
-                    auto row_of = [&](int base, int mod, int cur, int back, int s) -> int {
-                        if (s - back < 0) return BAND_NULL_ROW;
-                        int r = cur - back;
-                        if (r < 0) r += mod;
-                        return base + r;
-                    };
-                    // all-NULL row
-                    for (int i = tid; i < BAND_WP; i += NT) band_rows[BAND_NULL_ROW * BAND_WP + i] = NULL16;
-                    while (!band_fail && !band_break && !fb_end) {
-                        if (f_ak + r_ak >= max_antidiagonal) {
-                            band_break = true;
-                            break;
-                        }
-                        // ---- per-step table ----
-                        for (int i = tid; i < 2 * (BAND_T + 1) * BAND_TAB; i += NT) band_tab[i] = INT_MIN;
-                        cta_sync<NT>();
-                        const int m27 = S % BAND_MROWS, m3 = S % 3, m2 = S % 2;
-                        for (int d = 0; d < 2; ++d) {
-                            const SeqView& sv = (d == 0) ? svd[0] : svd[1];
-                            const int ce = (d == 0) ? cend[0] : cend[1];
-                            // span of the history rows, widened by the band length
-                            int mn = INT_MAX, mxk = INT_MIN;
-                            for (int j = 0; j < scope && S - j >= 0; ++j) {
-                                int sl = slotS - j;
-                                if (sl < 0) sl += rn16;
-                                const Meta16& q = meta16[d * rn16 + sl];
-#pragma unroll
-                                for (int c = 0; c < 5; ++c)
-                                    if (q.lo[c] <= q.hi[c]) {
-                                        mn = min(mn, q.lo[c]);
-                                        mxk = max(mxk, q.hi[c]);
-                                    }
-                            }
-                            if (mn > mxk) {  // every history row is empty: cannot happen in exact mode
-                                band_fail = true;
-                                break;
-                            }
-                            const int span_lo = mn - BAND_T, span_hi = mxk + BAND_T;
-                            for (int ka = span_lo; ka <= span_hi; ka += BAND_WT) {
-                                const int kb = min(ka + BAND_WT - 1, span_hi);
-                                const int base_k = ka - BAND_T;  // diagonal of shared-memory column 0
-                                // ---- load the history window (NULL outside each row's trimmed range) ----
-                                auto load_row = [&](int row, int c, int score) {
-                                    short* dst = band_rows + row * BAND_WP;
-                                    int lo_r = 1, hi_r = 0;
-                                    const short* src = ring16;
-                                    if (score >= 0) {
-                                        int sl = slotS - (S - score);
-                                        if (sl < 0) sl += rn16;
-                                        const Meta16& q = meta16[d * rn16 + sl];
-                                        lo_r = q.lo[c];
-                                        hi_r = q.hi[c];
-                                        src = ring16 + r16_off(d, sl, c);
-                                    }
-                                    for (int i = tid; i < BAND_WP; i += NT) {
-                                        const int k = base_k + i;
-                                        dst[i] = (k >= lo_r && k <= hi_r) ? src[k] : NULL16;
-                                    }
-                                };
-                                for (int j = 0; j < BAND_MROWS - 1; ++j) {
-                                    int r = m27 - j;
-                                    if (r < 0) r += BAND_MROWS;
-                                    load_row(r, AW_COMP_M, S - j);
-                                }
-                                for (int j = 0; j < 2; ++j) {
-                                    int r = m3 - j;
-                                    if (r < 0) r += 3;
-                                    load_row(BAND_MROWS + r, AW_COMP_I1, S - j);
-                                    load_row(BAND_MROWS + 3 + r, AW_COMP_D1, S - j);
-                                }
-                                if (TWO) {
-                                    load_row(BAND_MROWS + 6 + m2, AW_COMP_I2, S);
-                                    load_row(BAND_MROWS + 8 + m2, AW_COMP_D2, S);
-                                }
-                                cta_sync<NT>();
-                                // ---- BAND_T steps inside shared memory ----
-                                int c27 = m27, c3 = m3, c2 = m2, sl16 = slotS;
-                                for (int t = 1; t <= BAND_T; ++t) {
-                                    const int s = S + t;
-                                    c27 = (c27 + 1 == BAND_MROWS) ? 0 : c27 + 1;
-                                    c3 = (c3 + 1 == 3) ? 0 : c3 + 1;
-                                    c2 ^= 1;
-                                    sl16 = (sl16 + 1 == rn16) ? 0 : sl16 + 1;
-                                    const short* r_mx = band_rows + row_of(0, BAND_MROWS, c27, pen.x, s) * BAND_WP;
-                                    const short* r_mo1 = band_rows + row_of(0, BAND_MROWS, c27, pen.o1 + pen.e1, s) * BAND_WP;
-                                    const short* r_i1 = band_rows + row_of(BAND_MROWS, 3, c3, pen.e1, s) * BAND_WP;
-                                    const short* r_d1 = band_rows + row_of(BAND_MROWS + 3, 3, c3, pen.e1, s) * BAND_WP;
-                                    const short* r_mo2 = band_rows + (TWO ? row_of(0, BAND_MROWS, c27, pen.o2 + pen.e2, s) : BAND_NULL_ROW) * BAND_WP;
-                                    const short* r_i2 = band_rows + (TWO ? row_of(BAND_MROWS + 6, 2, c2, pen.e2, s) : BAND_NULL_ROW) * BAND_WP;
-                                    const short* r_d2 = band_rows + (TWO ? row_of(BAND_MROWS + 8, 2, c2, pen.e2, s) : BAND_NULL_ROW) * BAND_WP;
-                                    short* w_m = band_rows + c27 * BAND_WP;
-                                    short* w_i1 = band_rows + (BAND_MROWS + c3) * BAND_WP;
-                                    short* w_d1 = band_rows + (BAND_MROWS + 3 + c3) * BAND_WP;
-                                    short* w_i2 = band_rows + (BAND_MROWS + 6 + c2) * BAND_WP;
-                                    short* w_d2 = band_rows + (BAND_MROWS + 8 + c2) * BAND_WP;
-                                    short* g_m = ring16 + r16_off(d, sl16, AW_COMP_M);
-                                    short* g_i1 = ring16 + r16_off(d, sl16, AW_COMP_I1);
-                                    short* g_d1 = ring16 + r16_off(d, sl16, AW_COMP_D1);
-                                    short* g_i2 = ring16 + r16_off(d, sl16, TWO ? AW_COMP_I2 : AW_COMP_M);
-                                    short* g_d2 = ring16 + r16_off(d, sl16, TWO ? AW_COMP_D2 : AW_COMP_M);
-                                    int lo_c[5], hi_c[5];
-#pragma unroll
-                                    for (int c = 0; c < 5; ++c) lo_c[c] = hi_c[c] = INT_MIN;
-                                    int akM = INT_MIN, akAll = INT_MIN, endval = INT_MIN;
-                                    bool oob = false;
-                                    const unsigned utl = (unsigned)tlen, upl = (unsigned)plen;
-                                    // only diagonals the row can occupy at this step: [mn - t, mxk + t], inside the trapezoid
-                                    const int i_lo = max(t, mn - t - base_k), i_hi = min(BAND_WP - 1 - t, mxk + t - base_k);
-                                    // cells just outside the clipped range still hold an older row: later steps of this
-                                    // band read up to (BAND_T - t) + 1 columns beyond it, so NULL that margin
-                                    {
-                                        const int mg = BAND_T - t + 1;
-                                        if (tid < 2 * mg) {
-                                            const int i = (tid < mg) ? (i_lo - 1 - tid) : (i_hi + 1 + (tid - mg));
-                                            if (i >= 0 && i < BAND_WP) {
-                                                w_m[i] = NULL16;
-                                                w_i1[i] = NULL16;
-                                                w_d1[i] = NULL16;
-                                                if (TWO) {
-                                                    w_i2[i] = NULL16;
-                                                    w_d2[i] = NULL16;
-                                                }
-                                            }
-                                        }
-                                    }
-                                    constexpr int J = 4;  // cells per thread advanced in lockstep (independent chains)
-                                    for (int i0 = i_lo + tid; i0 <= i_hi; i0 += J * NT) {
-                                        int ii[J], kk[J], vm[J], vpre[J], vi1[J], vd1[J], vi2[J], vd2[J], ext[J];
-                                        bool act[J], more[J];
-#pragma unroll
-                                        for (int j = 0; j < J; ++j) {
-                                            act[j] = (i0 + j * NT) <= i_hi;
-                                            ii[j] = act[j] ? i0 + j * NT : i_lo;
-                                            kk[j] = base_k + ii[j];
-                                        }
-#pragma unroll
-                                        for (int j = 0; j < J; ++j) {
-                                            const int i = ii[j];
-                                            int i1 = max((int)r_mo1[i - 1], (int)r_i1[i - 1]) + 1;
-                                            const int d1 = max((int)r_mo1[i + 1], (int)r_d1[i + 1]);
-                                            int i2 = NULL16, d2 = NULL16, ins = i1, del = d1;
-                                            if (TWO) {
-                                                i2 = max((int)r_mo2[i - 1], (int)r_i2[i - 1]) + 1;
-                                                d2 = max((int)r_mo2[i + 1], (int)r_d2[i + 1]);
-                                                ins = max(i1, i2);
-                                                del = max(d1, d2);
-                                            }
-                                            int m = max(del, max((int)r_mx[i] + 1, ins));
-                                            vpre[j] = m;
-                                            if ((unsigned)m > utl || (unsigned)(m - kk[j]) > upl) m = NULL16;
-                                            vm[j] = m;
-                                            vi1[j] = (i1 < 0) ? (int)NULL16 : i1;  // all negative offsets are equivalent: stop the +1 drift
-                                            vd1[j] = d1;
-                                            vi2[j] = (i2 < 0) ? (int)NULL16 : i2;
-                                            vd2[j] = d2;
-                                        }
-#pragma unroll
-                                        for (int j = 0; j < J; ++j) {  // first extend round, branch-free
-                                            const bool valid = vm[j] >= 0;
-                                            extend_first<BITS>(sv, valid ? kk[j] : 0, valid ? vm[j] : 0, ext[j], more[j]);
-                                            more[j] = more[j] && valid;
-                                            if (valid) vm[j] += ext[j];
-                                        }
-#pragma unroll
-                                        for (int j = 0; j < J; ++j)  // long match runs (rare)
-                                            if (more[j]) vm[j] = extend_rest<BITS>(sv, kk[j], vm[j]);
-#pragma unroll
-                                        for (int j = 0; j < J; ++j) {
-                                            if (!act[j]) continue;
-                                            const int i = ii[j], k = kk[j], m = vm[j], i1 = vi1[j], d1 = vd1[j], i2 = vi2[j], d2 = vd2[j];
-                                            w_m[i] = (short)m;
-                                            w_i1[i] = (short)i1;
-                                            w_d1[i] = (short)d1;
-                                            if (TWO) {
-                                                w_i2[i] = (short)i2;
-                                                w_d2[i] = (short)d2;
-                                            }
-                                            if (k >= ka && k <= kb) {  // cells this tile owns
-                                                if (k >= kmin_alloc && k <= kmax_alloc) {
-                                                    g_m[k] = (short)m;
-                                                    g_i1[k] = (short)i1;
-                                                    g_d1[k] = (short)d1;
-                                                    if (TWO) {
-                                                        g_i2[k] = (short)i2;
-                                                        g_d2[k] = (short)d2;
-                                                    }
-                                                } else if (m >= 0 || i1 >= 0 || d1 >= 0 || i2 >= 0 || d2 >= 0) {
-                                                    oob = true;  // valid data outside the allocated diagonals
-                                                }
-                                                if (vpre[j] >= 0) akAll = max(akAll, 2 * vpre[j] - k);
-                                                if (m >= 0) {
-                                                    if (lo_c[0] == INT_MIN) lo_c[0] = -k;
-                                                    hi_c[0] = k;
-                                                    akM = max(akM, 2 * m - k);
-                                                }
-                                                auto track = [&](int c, int v) {
-                                                    if (v >= 0) {
-                                                        if ((unsigned)v > utl || (unsigned)(v - k) > upl) oob = true;
-                                                        if (lo_c[c] == INT_MIN) lo_c[c] = -k;
-                                                        hi_c[c] = k;
-                                                    }
-                                                };
-                                                track(AW_COMP_I1, i1);
-                                                track(AW_COMP_D1, d1);
-                                                if (TWO) {
-                                                    track(AW_COMP_I2, i2);
-                                                    track(AW_COMP_D2, d2);
-                                                }
-                                                if (k == k_end) endval = (ce == AW_COMP_M) ? m : (ce == AW_COMP_I1) ? i1 : (ce == AW_COMP_D1) ? d1 : (ce == AW_COMP_I2) ? i2 : d2;
-                                            }
-                                        }
-                                    }
-                                    int* tab = band_tab + (d * (BAND_T + 1) + t) * BAND_TAB;
-#pragma unroll
-                                    for (int c = 0; c < 5; ++c) {
-                                        if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
-                                        red_max<256>(tab, RED_HI + c, hi_c[c]);
-                                        red_max<256>(tab, RED_LO + c, lo_c[c]);
-                                    }
-                                    red_max<256>(tab, RED_AKM, akM);
-                                    red_max<256>(tab, RED_AKALL, akAll);
-                                    red_max<256>(tab, RED_END, endval);
-                                    if (__any_sync(0xffffffffu, oob) && (tid & 31) == 0) s_band_flag = 1;
-                                    cta_sync<NT>();
-                                }
-                                w_cells += (unsigned long long)BAND_T * (unsigned long long)(kb - ka + 1) * NCOMP;
-                            }
-                            w_steps += BAND_T;
-                        }
-                        cta_sync<NT>();
-                        if (band_fail || s_band_flag) {
-                            band_fail = true;
-                            break;
-                        }
-                        // ---- replay WFA2's alternation over the band's steps; publish the rows' metadata ----
-                        int sl = slotS;
-                        for (int t = 1; t <= BAND_T && !band_break && !fb_end; ++t) {
-                            sl = (sl + 1 == rn16) ? 0 : sl + 1;
-                            bool done_d[2];
-                            int ak_d[2];
-                            for (int d = 0; d < 2; ++d) {
-                                const int* tab = band_tab + (d * (BAND_T + 1) + t) * BAND_TAB;
-                                Meta16& q = meta16[d * rn16 + sl];
-#pragma unroll
-                                for (int c = 0; c < 5; ++c) {
-                                    const int h = tab[RED_HI + c], l = tab[RED_LO + c];
-                                    q.lo[c] = (h == INT_MIN) ? 1 : -l;
-                                    q.hi[c] = (h == INT_MIN) ? 0 : h;
-                                }
-                                q.akM = tab[RED_AKM];
-                                q.akAll = tab[RED_AKALL];
-                                done_d[d] = tab[RED_END] >= tlen;
-                                ak_d[d] = q.akM;
-                            }
-                            // forward step S+t
-                            score_f = S + t;
-                            f_ak = max(f_ak, max(0, done_d[0] ? 0 : ak_d[0]));
-                            last_forward = true;
-                            if (AW_BIALIGN_PHASE1_END_REACHED_RETURNS && done_d[0]) {
-                                fb_end = true;
-                                break;
-                            }
-                            if (f_ak + r_ak >= max_antidiagonal) {
-                                band_break = true;  // reverse stays at S+t-1
-                                break;
-                            }
-                            // reverse step S+t
-                            score_r = S + t;
-                            r_ak = max(r_ak, max(0, done_d[1] ? 0 : ak_d[1]));
-                            last_forward = false;
-                            if (AW_BIALIGN_PHASE1_END_REACHED_RETURNS && done_d[1]) {
-                                fb_end = true;
-                                break;
-                            }
-                            if (f_ak + r_ak >= max_antidiagonal) band_break = true;
-                        }
-                        if (!band_break && !fb_end) {
-                            S += BAND_T;
-                            slotS += BAND_T;
-                            if (slotS >= rn16) slotS -= rn16;
-                        }
-                        cta_sync<NT>();
-                    }
-                    if (band_fail) {
-                        cyc[5] += 1;
-                        // redo phase 1 on the generic path from score 0 (rows 0 are still in the int32 ring)
-                        score_f = score_r = 0;
-                        f_ak = max(0, ring_meta[0 * ring_n + 0].akM);
-                        r_ak = max(0, ring_meta[1 * ring_n + 0].akM);
-                        last_forward = false;
-                        cur_slot[0] = cur_slot[1] = 0;
-                    } else {
-                        band_done = true;
-                        if (!fb_end) {
-                            // ---- hand-over: last `scope` rows of each direction -> generic int32 ring ----
-                            for (int d = 0; d < 2; ++d) {
-                                const int sd = (d == 0) ? score_f : score_r;
-                                int sl_top = slotS + (sd - S);
-                                if (sl_top >= rn16) sl_top -= rn16;
-                                for (int j = 0; j < scope && sd - j >= 0; ++j) {
-                                    int sl16 = sl_top - j;
-                                    if (sl16 < 0) sl16 += rn16;
-                                    const int sl32 = (sd - j) % ring_n;
-                                    const Meta16& q = meta16[d * rn16 + sl16];
-                                    SlotMeta& mt = ring_meta[d * ring_n + sl32];
-#pragma unroll
-                                    for (int c = 0; c < 5; ++c) {
-                                        mt.lo[c] = q.lo[c];
-                                        mt.hi[c] = q.hi[c];
-                                        if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
-                                        const short* src = ring16 + r16_off(d, sl16, c);
-                                        WS* dst = ws + ring_off(d, sl32, c);
-                                        for (int k = q.lo[c] + tid; k <= q.hi[c]; k += NT) {
-                                            const int v = src[k];
-                                            dst[k] = to_ws<WS>(v < 0 ? AW_NULLV : v);
-                                        }
-                                    }
-                                    mt.akM = q.akM;
-                                    mt.akAll = q.akAll;
-                                }
-                                cur_slot[d] = sd % ring_n;
-                            }
-                            cta_sync<NT>();
-                        }
-                    }
-                }
                 // ---- phase 1: forward step s_f+1 and (speculative) reverse step s_r+1 share one barrier ----
-                while (!band_done && !fb_end && status == ST_OK) {
+                while (!fb_end && status == ST_OK) {
                     if (f_ak + r_ak >= max_antidiagonal) break;
                     const int slot_f = next_slot(cur_slot[0]), slot_r = next_slot(cur_slot[1]);
-                    const Range rf = launch_dir(0, score_f + 1, slot_f);
-                    const Range rr = launch_dir(1, score_r + 1, slot_r);
-                    cta_sync<NT>();
-                    bool done = finish_dir(0, slot_f, rf);
-                    const int akM_f = ring_meta[0 * ring_n + slot_f].akM;
-                    const bool done_r = finish_dir(1, slot_r, rr);
-                    const int akM_r = ring_meta[1 * ring_n + slot_r].akM;
+                    bool done, done_r;
+                    int akM_f, akM_r;
+                    if constexpr (VEC) {
+                        // half of the warps advance the forward wavefront, the other half the reverse one
+                        constexpr int HW = NT / 64;
+                        const int warp = tid >> 5;
+                        if (warp < HW) v_launch(0, 0, score_f + 1, slot_f, warp, HW, false, svd[0], k_end, cend[0]);
+                        else v_launch(1, ring_n, score_r + 1, slot_r, warp - HW, HW, false, svd[1], k_end, cend[1]);
+                        cta_sync<NT>();
+                        done = v_finish(0, 0, slot_f, plen, tlen, k_end, cend[0], akM_f);
+                        done_r = v_finish(1, ring_n, slot_r, plen, tlen, k_end, cend[1], akM_r);
+                    } else {
+                        const Range rf = launch_dir(0, score_f + 1, slot_f);
+                        const Range rr = launch_dir(1, score_r + 1, slot_r);
+                        cta_sync<NT>();
+                        done = finish_dir(0, slot_f, rf);
+                        akM_f = ring_meta[0 * ring_n + slot_f].akM;
+                        done_r = finish_dir(1, slot_r, rr);
+                        akM_r = ring_meta[1 * ring_n + slot_r].akM;
+                    }
                     rotate_red();
                     if (status != ST_OK) break;
                     // commit forward
@@ -1291,9 +1460,17 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                 // one committed step of direction d (phase 2): cells, barrier, finish
                 auto step_dir = [&](int d, int s) -> bool {
                     const int slot = next_slot(cur_slot[d]);
-                    const Range r = launch_dir(d, s, slot);
-                    cta_sync<NT>();
-                    const bool done = finish_dir(d, slot, r);
+                    bool done;
+                    if constexpr (VEC) {
+                        int ak;
+                        v_launch(d, d * ring_n, s, slot, tid >> 5, NT / 32, false, d == 0 ? svd[0] : svd[1], k_end, d == 0 ? cend[0] : cend[1]);
+                        cta_sync<NT>();
+                        done = v_finish(d, d * ring_n, slot, plen, tlen, k_end, d == 0 ? cend[0] : cend[1], ak);
+                    } else {
+                        const Range r = launch_dir(d, s, slot);
+                        cta_sync<NT>();
+                        done = finish_dir(d, slot, r);
+                    }
                     rotate_red();
                     cur_slot[d] = slot;
                     return done;
@@ -1352,12 +1529,13 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                 }
             }
 
+//@region base case
             // =========== K7: wavefront_bialign_base: full-history WFA + backtrace ===========
             {
                 ++w_base;
                 lap(5);
                 const SeqView sv = SeqView{pw, tw, sp.pb, sp.tb, plen, tlen, false};
-                long long hist_used = 0;
+                hist_used = 0;
                 // component block of a history wavefront: element (c,k) at ws[hist_off(off,width,clo,c) + k]
                 auto hist_off = [&](int off, int width, int clo, int c) -> int { return hist_base + off + comp_idx(c) * width - clo; };
                 auto write_hist_meta = [&](int s, const SlotMeta& m) {
@@ -1368,9 +1546,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                             g[c] = m.lo[c];
                             g[5 + c] = m.hi[c];
                         }
-                        g[10] = m.clo;
-                        g[11] = m.width;
-                        g[12] = m.off;
+                        g[10] = m.off;
+                        g[11] = m.cstride;
                     }
                 };
                 auto slot_back = [&](int slot, int back) -> int {
@@ -1380,6 +1557,27 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                 StepOut so;
                 int score = 0, slot = 0;
                 bool done;
+                if constexpr (VEC) {
+                    int ak;
+                    done = v_init_row(0, 0, true, sv, sp.cb, sp.ce, k_end, ak);
+                    write_hist_meta(0, ring_meta[0]);
+                    rotate_red();
+                    while (!done) {
+                        ++score;
+                        slot = (slot + 1 == ring_n) ? 0 : slot + 1;
+                        if (score >= P.hist_max_scores) {
+                            status = ST_FAIL_WORKSPACE;
+                            break;
+                        }
+                        const VRange rg = v_launch(0, 0, score, slot, tid >> 5, NT / 32, true, sv, k_end, sp.ce);
+                        hist_used += (long long)NCOMP * rg.width;
+                        cta_sync<NT>();
+                        done = v_finish(0, 0, slot, plen, tlen, k_end, sp.ce, ak);
+                        if (status != ST_OK) break;
+                        write_hist_meta(score, ring_meta[slot]);
+                        rotate_red();
+                    }
+                } else {
                 {  // score 0
                     int* r = red[0][red_i];
                     SlotMeta& mt = ring_meta[0];
@@ -1399,9 +1597,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                     so.endval = r[RED_END];
                     so.ambiguous = false;
                     store_meta(mt, so);
-                    mt.clo = 0;
-                    mt.width = 1;
-                    mt.off = 0;
+                    mt.off = hist_base;
+                    mt.cstride = 1;
                     hist_used = NCOMP;
                     write_hist_meta(0, mt);
                     rotate_red();
@@ -1424,7 +1621,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                             return w;
                         }
                         const SlotMeta& m = ring_meta[slot_back(slot, back)];
-                        w.off = hist_off(m.off, m.width, m.clo, c);
+                        w.off = m.off + comp_idx(c) * m.cstride;
                         w.lo = m.lo[c];
                         w.hi = m.hi[c];
                         return w;
@@ -1451,6 +1648,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                         write_hist_meta(score, mt);
                         continue;
                     }
+                    const int clo = lo;
                     const int width = hi - lo + 1;
                     if (hist_used + (long long)NCOMP * width > (long long)P.hist_ints) {
                         status = ST_FAIL_WORKSPACE;
@@ -1460,25 +1658,26 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                     hist_used += (long long)NCOMP * width;
                     int out[5];
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) out[c] = hist_off(off, width, lo, (TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M);
+                    for (int c = 0; c < 5; ++c) out[c] = hist_off(off, width, clo, (TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M);
                     wf_cells<NT, BITS, TWO, WS>(ws, in, out, lo, hi, sv, k_end, sp.ce, red[0][red_i]);
                     cta_sync<NT>();
                     wf_finish<TWO>(red[0][red_i], lo, hi, so);
                     if (so.ambiguous) wf_rescan<NT, TWO, WS>(ws, out, lo, hi, plen, tlen, red[0][red_i], so);
-                    w_cells += (unsigned long long)width * NCOMP;
+                    w_cells += (unsigned long long)(hi - lo + 1) * NCOMP;
                     store_meta(mt, so);
-                    mt.clo = lo;
-                    mt.width = width;
-                    mt.off = off;
+                    mt.off = hist_off(off, width, clo, AW_COMP_M);
+                    mt.cstride = width;
                     write_hist_meta(score, mt);
                     rotate_red();
                     done = end_reached(so, sp.ce, k_end, tlen);
+                }
                 }
                 if (status != ST_OK) break;
                 w_maxbase = max(w_maxbase, (unsigned)score);
                 cta_sync<NT>();  // history + meta visible to warp 0
                 lap(2);
 
+//@region backtrace
                 // ---- wavefront_backtrace_affine by warp 0: lanes evaluate the candidates ----
                 unsigned n_leaf = 0;  // runs pushed (reverse order) into leaf_runs; uniform within warp 0
                 if (tid < 32) {
@@ -1521,7 +1720,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
                                 const int* g = hist_meta + (size_t)ss * HIST_META_INTS;
                                 const int kk = k + dk;
                                 if (g[comp_src] <= kk && kk <= g[5 + comp_src]) {
-                                    const int val = ws[hist_off(g[12], g[11], g[10], comp_src) + kk];
+                                    const int val = ws[g[10] + comp_idx(comp_src) * g[11] + kk];
                                     if (val >= 0) cand_v = ((val + add) << AW_BT_TYPE_BITS) | bt;
                                 }
                             }
@@ -1602,6 +1801,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256) ? AW_CTAS_PER_SM_256 : (NT == 
             }
         }  // DFS over sub-problems
 
+//@region emit
         // =========== K8: statistics, score, PAF text ===========
         cta_sync<NT>();
         const unsigned nruns = (status == ST_OK) ? s_nruns : 0;
