@@ -113,7 +113,7 @@ struct aw_ctx {
     bool have_stranded = false;
     std::map<std::pair<int, uint32_t>, SketchSet*> canonical;
     // grow-only per-launch workspace (one launch in flight per context)
-    DevBuf ws_main, ws_hist_meta, ws_runs;
+    DevBuf ws_main, ws_hist_meta, ws_runs, ws_blk;
 };
 
 struct aw_batch {
@@ -226,6 +226,7 @@ extern "C" void aw_destroy(aw_ctx* c) {
     c->d_id_off.release();
     c->ws_main.release();
     c->ws_hist_meta.release();
+    c->ws_blk.release();
     c->ws_runs.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -236,7 +237,7 @@ extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
     std::string k(key);
     if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
     else if (k == "threads_per_cta") {
-        if (value != 0 && value != 32 && value != 128 && value != 256) return AW_EINVAL;
+        if (value != 0 && value != 32 && value != 64 && value != 128 && value != 256) return AW_EINVAL;
         c->threads_per_cta = (int)value;
     } else if (k == "max_wavefront_width") c->max_w = value;
     else if (k == "hist_mb") c->hist_mb = value;
@@ -619,6 +620,7 @@ struct LaunchCfg {
     unsigned long long ws_ints, hist_ints, runs_cap;
     bool ws16;
     int hist_max_scores;
+    int blk_cap;
 };
 
 template <int NT, int BITS, bool TWO, class WS>
@@ -634,7 +636,7 @@ cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStrea
 
 cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bool ws16, int grid, cudaStream_t st) {
     const int scope = P.pen.scope;
-    size_t smem = sizeof(awk::SlotMeta) * 2 * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt;
+    size_t smem = sizeof(awk::SlotMeta) * 2 * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt + sizeof(int) * (15 * scope + 4);
 #define AW_CASE(NT_, BITS_, TWO_, WS_, W16_) \
     if (nt == NT_ && bits == BITS_ && two == TWO_ && ws16 == W16_) return launch_align<NT_, BITS_, TWO_, WS_>(P, grid, smem, st);
 #ifndef AW_FAST_BUILD  // dev builds (-DAW_FAST_BUILD) keep only the two-piece 2-bit int16 kernels
@@ -659,6 +661,7 @@ cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bo
 #endif
     AW_CASE(256, 2, true, short, true)
     AW_CASE(128, 2, true, short, true)
+    AW_CASE(64, 2, true, short, true)
 #undef AW_CASE
     return cudaErrorInvalidValue;
 }
@@ -681,7 +684,9 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     // int16 storage: every offset (incl. out-of-bounds I/D drift, <= 2*tlen+plen) must stay below 32000
     const bool ws16 = c->ws16 && nt >= 64 && (2 * max_t + max_p < 32000) && (2 * max_p + max_t < 32000);
     const uint64_t epi = ws16 ? 2 : 1;  // elements per int
-    uint64_t ring_ints = ((2ull * (pen.scope + 1) * ncomp + 1) * W + epi - 1) / epi;  // + the all-NULL row of the int16 path
+    // + the all-NULL row and the compact I/D rings of the int16 path (aw_wfa.cuh: null_base, cmp_base)
+    const uint64_t cmp_rows = 2ull * (2 * (pen.e1 + 1) + (pen.two_piece ? 2 * (pen.e2 + 1) : 0));
+    uint64_t ring_ints = ((2ull * (pen.scope + 1) * ncomp + 1 + cmp_rows) * W + epi - 1) / epi;
     if (ring_ints >= 0x7f000000ull) {
         aw_set_error("wavefront ring of %llu ints per CTA exceeds the 32-bit workspace index", (unsigned long long)ring_ints);
         return AW_EUNSUPPORTED;
@@ -709,8 +714,10 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     cfg->ws16 = ws16;
     cfg->runs_cap = runs_cap;
     cfg->hist_max_scores = hist_max_scores;
+    cfg->blk_cap = (int)(W / (awk::VBLOCK_CHUNKS * 4) + 2);  // blocks of >= 30 x 4 diagonals (AW_CPT >= 4)
     int rc;
     if ((rc = c->ws_main.ensure(grid * ws_ints * 4)) ||
+        (rc = c->ws_blk.ensure(grid * 2ull * (pen.scope + 1) * (uint64_t)cfg->blk_cap * 2 * 4)) ||
         (rc = c->ws_hist_meta.ensure(grid * (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4)) || (rc = c->ws_runs.ensure(grid * runs_cap * 8)))
         return rc;
     return AW_OK;
@@ -732,6 +739,8 @@ void fill_params(aw_ctx* c, aw_batch* b, const AwPen& pen, const LaunchCfg& cfg,
     P->W = cfg.W;
     P->hist_ints = (int)std::min<unsigned long long>(cfg.hist_ints, 0x7fffffffull);
     P->ws_hist_meta = c->ws_hist_meta.as<int>();
+    P->ws_blk = c->ws_blk.as<int>();
+    P->blk_cap = cfg.blk_cap;
     P->hist_max_scores = cfg.hist_max_scores;
     P->ws_runs = c->ws_runs.as<uint32_t>();
     P->runs_cap = cfg.runs_cap;

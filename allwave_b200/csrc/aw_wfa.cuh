@@ -19,6 +19,15 @@ namespace awk {
 #ifndef AW_CPT
 #define AW_CPT 8
 #endif
+#ifndef AW_PREFETCH_STEPS
+#define AW_PREFETCH_STEPS 0  // int16 path: L2 prefetch distance (score steps) for the old M rows; 0 = off (measured: no gain on C2)
+#endif
+#ifndef AW_COMPACT_ID_RINGS
+// int16 path: 1 = far from the overlap phase, I/D rows rotate through small rings (extension distance + 1 rows) so that they
+// are overwritten while still in L2.  Measured on C2 (592 pairs in flight): HBM writes -28 % but no speed-up (the M rings
+// alone overflow L2), and the extra addressing costs ~10 %, so it is off by default.
+#define AW_COMPACT_ID_RINGS 0
+#endif
 #ifndef AW_REGS
 #define AW_REGS 128  // register budget per thread of the CTA-per-pair kernels: resident CTAs per SM = 65536 / (NT * AW_REGS)
 #endif
@@ -48,6 +57,9 @@ struct SlotMeta {
     int off;            // workspace element offset of (component 0, k = 0) of this wavefront
     int cstride;        // elements between consecutive components
     int wlo, whi;       // int16 rows: diagonals that read back correctly without masking (NULL outside the trimmed range)
+    int coff[5];        // int16 rows: element offset of (component c, k = 0), indexed by AW_COMP_*
+    int full;           // int16 ring rows: 1 = the I/D components sit in the full ring (readable for `scope` steps), 0 = compact ring
+    int bk0, nblk;      // int16 ring rows: first diagonal of block 0 and number of blocks of the per-block maxima
 };
 
 struct In {
@@ -85,6 +97,8 @@ struct KParams {
     unsigned long long ws_ints_per_cta;
     int W;                   // allocated diagonals per ring wavefront
     int hist_ints;           // history arena size (ints)
+    int* ws_blk;             // int16 path: [cta][2 directions][scope+1 slots][blk_cap][2] per-block (akM, akAll) maxima
+    int blk_cap;
     int* ws_hist_meta;       // [cta][hist_max_scores][HIST_META_INTS]
     int hist_max_scores;
     uint32_t* ws_runs;       // [cta][2][runs_cap]: pair runs, then leaf scratch
@@ -347,31 +361,25 @@ __device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7],
     red_max<NT>(red, RED_AKALL, akAll);
 }
 
-// ---- direction-generic match extension (one code path for the forward and the reverse aligner) ----
-// dir = +1 / rev = 0: symbols pos, pos+1, ... ; dir = -1 / rev = 1: symbols pos, pos-1, ...  In both cases the
-// returned word holds the first symbol to compare in its least significant bits.
-template <int BITS>
-__device__ __forceinline__ uint32_t load_dir(const uint32_t* __restrict__ w, int pos, int rev) {
-    constexpr int SPW = 32 / BITS;
-    const int idx = (int)((unsigned)pos / SPW) - rev;
-    const int sh = (int)(((unsigned)pos % SPW) + rev) * BITS;  // forward [0, 32-BITS], reverse [BITS, 32]
-    const uint32_t x = __funnelshift_rc(w[idx], w[idx + 1], sh);
-    return x;
+// ---- match extension of the int16 path: 2-bit sequences staged in shared memory as overlapping word
+// pairs, entry i = (w[i], w[i+1]), so one 8-byte load + one funnel shift yields the 16 symbols that start
+// at any position.  The reverse aligner reads reversed copies (wavefront_sequences_init_* keeps reversed
+// copies too), so there is only a forward code path.
+constexpr int SEQ2_ENTRIES = 2720;  // uint2 entries for 2 x (pattern + text): plen + tlen <= 21696 symbols
+__device__ __forceinline__ uint32_t load16(const uint2* __restrict__ s2, int pos) {
+    const uint2 e = s2[(unsigned)pos >> 4];
+    return __funnelshift_r(e.x, e.y, (pos & 15) * 2);
 }
-// number of matching symbols (<= maxlen) from (v,h) in the aligner's direction; first = only one word
-template <int BITS>
-__device__ __forceinline__ int lcp_dir(const uint32_t* __restrict__ pw, const uint32_t* __restrict__ tw, int pp, int tp, int rev, int maxlen) {
-    constexpr int SPW = 32 / BITS;
-    const int dir = 1 - 2 * rev;
+// matching symbols from (pp, tp), at most maxlen
+__device__ __forceinline__ int lcp2(const uint2* __restrict__ p2, const uint2* __restrict__ t2, int pp, int tp, int maxlen) {
     int n = 0;
     while (n < maxlen) {
-        uint32_t x = load_dir<BITS>(pw, pp + dir * n, rev) ^ load_dir<BITS>(tw, tp + dir * n, rev);
+        const uint32_t x = load16(p2, pp + n) ^ load16(t2, tp + n);
         if (x) {
-            if (rev) x = __brev(x);  // symbol pos sits in the most significant bits of a reverse word
-            n += (__ffs(x) - 1) / BITS;
+            n += __clz(__brev(x)) >> 1;
             break;
         }
-        n += SPW;
+        n += 16;
     }
     return min(n, maxlen);
 }
@@ -396,6 +404,10 @@ __device__ __forceinline__ int lcp_dir(const uint32_t* __restrict__ pw, const ui
 // hence non-null).  Rows that do hold such a cell raise RED_OOB and are trimmed exactly by
 // wf_rescan after the barrier.
 constexpr int VMARGIN = 48;
+// Every warp iteration of the cell loop (VBLOCK diagonals) also records its own maxima of the two antidiagonal bounds
+// (akM, akAll).  The overlap test uses them to skip (candidate, block) pairs that cannot contain a meeting point, which
+// is almost all of them: the wavefronts only touch near the optimal path.
+constexpr int VBLOCK_CHUNKS = 30;  // = chunks owned per warp iteration
 constexpr int VBIG = 1 << 28;
 
 template <int CPT>
@@ -446,20 +458,25 @@ __device__ __forceinline__ int half_hi(uint32_t w) { return (int)w >> 16; }
 // Called by the `gnw` warps of a group (gwarp = this warp's index in the group).
 //   in_off  : lane i < 7 holds the element offset (k = 0) of input i (IN_*); the NULL row when absent
 //   dsc     : warp-private shared memory, dsc[i] / dsc[8+i] = trimmed lo / hi of input i (empty: lo > hi)
-//   out_off : element offset (k = 0) of output component 0, components are `cstride` apart
+//   ocoff   : shared memory, element offset (k = 0) of every output component (SlotMeta::coff)
 //   [lo,hi] : computed range; [fast_lo,fast_hi] : diagonals every input reads back unmasked
 //   [wlo,whi]: what this row must leave readable (computed chunks + NULL margin, clipped to the allocation)
 template <int BITS, bool TWO, int CPT>
-__device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, const int* dsc, int out_off, int cstride, int lo, int hi, int fast_lo, int fast_hi,
-                                        int wlo, int whi, const uint32_t* __restrict__ s_pw, const uint32_t* __restrict__ s_tw, int s_p0, int s_t0, int s_plen,
-                                        int s_tlen, int rev, int k_end, int comp_end, int* red, int gwarp, int gnw) {
+__device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, const int* dsc, const int* ocoff, int lo, int hi, int fast_lo, int fast_hi,
+                                        int wlo, int whi, const uint2* __restrict__ s_p2, const uint2* __restrict__ s_t2, int s_p0, int s_t0, int s_plen,
+                                        int s_tlen, int k_end, int comp_end, int* red, int gwarp, int gnw, int pf_off, int* __restrict__ blk) {
+    static_assert(BITS == 2, "the int16 path reads 2-bit sequences");
+    // pf_off: lanes IN_MO1 / IN_MO2 hold the element offset of the M row those inputs will be two steps from now
+    // (or -1): rows that old have usually left L2, so their lines are requested now (prefetch.global.L2)
+    int pf1 = -1, pf2 = -1;
+    if (AW_PREFETCH_STEPS > 0) {
+        pf1 = __shfl_sync(0xffffffffu, pf_off, IN_MO1);
+        if (TWO) pf2 = __shfl_sync(0xffffffffu, pf_off, IN_MO2);
+    }
     constexpr int VW = CPT / 2;
     constexpr int SH = (CPT == 8) ? 3 : (CPT == 4 ? 2 : 1);
-    constexpr int OWN = 30;  // chunks owned per warp iteration (lanes 1..30)
+    constexpr int OWN = VBLOCK_CHUNKS;  // chunks owned per warp iteration (lanes 1..30)
     const int lane = threadIdx.x & 31;
-    constexpr int SPW = 32 / BITS;
-    const unsigned tlen = (unsigned)s_tlen, plen = (unsigned)s_plen;
-    const int dir = 1 - 2 * rev;
     const int o_mx = __shfl_sync(0xffffffffu, in_off, IN_MX), o_mo1 = __shfl_sync(0xffffffffu, in_off, IN_MO1);
     const int o_i1e = __shfl_sync(0xffffffffu, in_off, IN_I1E), o_d1e = __shfl_sync(0xffffffffu, in_off, IN_D1E);
     int o_mo2 = 0, o_i2e = 0, o_d2e = 0;
@@ -469,19 +486,28 @@ __device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, cons
         o_d2e = __shfl_sync(0xffffffffu, in_off, IN_D2E);
     }
     const int c_lo = lo >> SH, c_hi = hi >> SH;  // arithmetic shift = floor
-    const int o_m = out_off, o_i1 = out_off + cstride, o_i2 = out_off + 2 * cstride, o_d1 = out_off + (TWO ? 3 : 2) * cstride, o_d2 = out_off + 4 * cstride;
+    const int o_m = ocoff[AW_COMP_M], o_i1 = ocoff[AW_COMP_I1], o_i2 = ocoff[AW_COMP_I2], o_d1 = ocoff[AW_COMP_D1], o_d2 = ocoff[AW_COMP_D2];
     int akM = INT_MIN, akAll = INT_MIN;
     bool oob = false;
-    for (int cw = c_lo + gwarp * OWN; cw <= c_hi; cw += gnw * OWN) {
+    int bidx = gwarp;
+    for (int cw = c_lo + gwarp * OWN; cw <= c_hi; cw += gnw * OWN, bidx += gnw) {
+        int akM_b = INT_MIN, akAll_b = INT_MIN;
         const int c = cw - 1 + lane;
         const int kc = c << SH;
         const bool own = (lane >= 1) && (lane <= OWN) && (c <= c_hi);
         const bool fast = (kc >= fast_lo) && (kc + CPT - 1 <= fast_hi);
         uint32_t mx[VW], tI1[VW], tD1[VW], tI2[VW], tD2[VW];
-        {
+        if (c > c_hi + 1) {  // neither owned nor a neighbour's halo
+#pragma unroll
+            for (int i = 0; i < VW; ++i) mx[i] = tI1[i] = tD1[i] = tI2[i] = tD2[i] = NULL16X2;
+        } else {
             uint32_t mo[VW], ie[VW], de[VW], mo2[VW], ie2[VW], de2[VW];
             if (fast) {
                 const short* pk = ws + kc;
+                if (AW_PREFETCH_STEPS > 0) {
+                    if (pf1 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + pf1));
+                    if (pf2 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + pf2));
+                }
                 ld_vec<CPT>(pk + o_mx, mx);
                 ld_vec<CPT>(pk + o_mo1, mo);
                 ld_vec<CPT>(pk + o_i1e, ie);
@@ -553,41 +579,41 @@ __device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, cons
                     if ((j >> 1) == i) wsel = src[i];
                 red[RED_END] = (j & 1) ? half_hi(wsel) : half_lo(wsel);
             }
-            int mm[CPT], nn[CPT];
+            int mm[CPT];
             unsigned more = 0;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int k = kc + j;
                 const int m = (j & 1) ? half_hi(vM[j >> 1]) : half_lo(vM[j >> 1]);
-                const bool valid = !((unsigned)m > tlen || (unsigned)(m - k) > plen);
+                const int v = m - k;
+                const int maxlen = min(s_plen - v, s_tlen - m);
+                const bool valid = (m | v | maxlen) >= 0;  // 0 <= h <= tlen and 0 <= v <= plen
                 if (m >= 0) {
-                    akAll = max(akAll, 2 * m - k);  // m (pre-null) dominates every component at k
+                    akAll_b = max(akAll_b, m + v);  // 2*off - k; m (pre-null) dominates every component at k
                     oob = oob || !valid;
                 }
-                mm[j] = valid ? m : -1;
-                // first round of the extension (one word), branch-free; invalid cells compare position 0
-                const int maxlen = valid ? min(s_plen - (m - k), s_tlen - m) : 0;
-                const int v = (maxlen > 0) ? m - k : 0, h = (maxlen > 0) ? m : 0;  // nothing to compare: keep the (unused) loads inside the sequences
-                uint32_t x = load_dir<BITS>(s_pw, s_p0 + dir * v, rev) ^ load_dir<BITS>(s_tw, s_t0 + dir * h, rev);
-                if (rev) x = __brev(x);
-                const int cnt = x ? (__ffs(x) - 1) / BITS : SPW;
-                nn[j] = min(cnt, maxlen);
-                if (x == 0 && maxlen > SPW) more |= 1u << j;
+                // first round of the extension (16 symbols), branch-free; invalid cells compare position 0
+                const uint32_t x = load16(s_p2, s_p0 + (valid ? v : 0)) ^ load16(s_t2, s_t0 + (valid ? m : 0));
+                const int cnt = __clz(__brev(x)) >> 1;  // 16 when the whole word matches
+                mm[j] = valid ? m + min(cnt, maxlen) : -1;
+                if (valid && x == 0 && maxlen > 16) more |= 1u << j;
             }
+            while (more) {  // long match runs: continue word by word, one cell at a time (kept small: instruction-cache footprint)
+                const int j = __ffs(more) - 1;
+                more &= more - 1;
+                int h = mm[0];
 #pragma unroll
-            for (int j = 0; j < CPT; ++j) mm[j] += nn[j];
-            if (more) {  // long match runs: continue word by word
+                for (int q = 1; q < CPT; ++q)
+                    if (j == q) h = mm[q];
+                const int v = h - (kc + j);
+                h += lcp2(s_p2, s_t2, s_p0 + v, s_t0 + h, min(s_plen - v, s_tlen - h));
 #pragma unroll
-                for (int j = 0; j < CPT; ++j) {
-                    if (more & (1u << j)) {
-                        const int v = mm[j] - (kc + j), h = mm[j];
-                        mm[j] += lcp_dir<BITS>(s_pw, s_tw, s_p0 + dir * v, s_t0 + dir * h, rev, min(s_plen - v, s_tlen - h));
-                    }
-                }
+                for (int q = 0; q < CPT; ++q)
+                    if (j == q) mm[q] = h;
             }
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                if (mm[j] >= 0) akM = max(akM, 2 * mm[j] - (kc + j));
+                if (mm[j] >= 0) akM_b = max(akM_b, 2 * mm[j] - (kc + j));
                 else mm[j] = NULL16;
                 if (comp_end == AW_COMP_M && kc + j == k_end) red[RED_END] = mm[j];
             }
@@ -595,6 +621,13 @@ __device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, cons
             for (int i = 0; i < VW; ++i) vM[i] = __byte_perm((uint32_t)mm[2 * i], (uint32_t)mm[2 * i + 1], 0x5410);
             st_vec<CPT>(pk + o_m, vM);
         }
+        if (blk != nullptr) {
+            akM_b = __reduce_max_sync(0xffffffffu, akM_b);
+            akAll_b = __reduce_max_sync(0xffffffffu, akAll_b);
+            if (lane == 0) *reinterpret_cast<int2*>(blk + 2 * bidx) = make_int2(akM_b, akAll_b);
+        }
+        akM = max(akM, akM_b);
+        akAll = max(akAll, akAll_b);
     }
     // NULL margin either side of the computed chunks (clipped to [wlo,whi]), by the group's last warp
     if (gwarp == gnw - 1) {
@@ -604,10 +637,11 @@ __device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, cons
 #pragma unroll
         for (int i = 0; i < VW; ++i) nullv[i] = NULL16X2;
         for (int i = lane; i < 2 * MG * NCOMP; i += 32) {
-            const int comp = i / (2 * MG), j = i - comp * (2 * MG);
+            const int ci = i / (2 * MG), j = i - ci * (2 * MG);
+            const int comp = TWO ? ci : (ci == 2 ? AW_COMP_D1 : ci);
             const int c = (j < MG) ? (c_lo - MG + j) : (c_hi + 1 + (j - MG));
             const int kc = c << SH;
-            if (kc >= wlo && kc + CPT - 1 <= whi) st_vec<CPT>(ws + out_off + comp * cstride + kc, nullv);
+            if (kc >= wlo && kc + CPT - 1 <= whi) st_vec<CPT>(ws + ocoff[comp] + kc, nullv);
         }
     }
     akM = __reduce_max_sync(0xffffffffu, akM);
@@ -764,7 +798,7 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
 template <int NT, int BITS, bool TWO, class WS>
 __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const KParams P) {
     constexpr int NCOMP = TWO ? 5 : 3;
-    constexpr bool VEC = (sizeof(WS) == 2) && (NT >= 64);  // chunk-vectorised int16 cell loop
+    constexpr bool VEC = (sizeof(WS) == 2) && (NT >= 64) && (BITS == 2);  // chunk-vectorised int16 cell loop
     constexpr int CPT = AW_CPT;                            // diagonals per thread in that loop
     constexpr int RALIGN = VEC ? 8 : 1;                    // row alignment (elements)
     extern __shared__ unsigned long long smem_raw[];
@@ -773,24 +807,37 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     SlotMeta* ring_meta = reinterpret_cast<SlotMeta*>(smem_raw);                                     // [2][ring_n]
     int* cand = reinterpret_cast<int*>(ring_meta + 2 * ring_n);                                     // [scope*5] candidate tests
     int* hitk = cand + scope * 5;                                                                    // [scope*5] first hit per candidate
-    unsigned long long* scanbuf = reinterpret_cast<unsigned long long*>(hitk + scope * 5);  // [NT]; 8-byte aligned: 60*2*ring_n + 40*scope
+    unsigned long long* scanbuf = reinterpret_cast<unsigned long long*>(hitk + scope * 5);  // [NT]; 8-byte aligned: sizeof(SlotMeta)*2*ring_n + 40*scope
+    int* cklo = reinterpret_cast<int*>(scanbuf + NT);                                      // [scope*5] first diagonal of a candidate's scan range
+    int* ckhi = cklo + scope * 5;                                                          // [scope*5] last diagonal
+    int* cpre = ckhi + scope * 5;                                                          // [scope*5+1] first warp chunk of a candidate
     __shared__ int red[2][3][NRED];
     __shared__ SubProblem stack[MAX_STACK];
     __shared__ unsigned s_next;
     __shared__ unsigned s_nruns;
-    __shared__ int s_ncand;
+    __shared__ int s_ncand, s_nchunk;
     __shared__ unsigned long long s_acc[8];
     __shared__ unsigned long long s_text_off, s_bytes_off;
-    __shared__ uint32_t s_seq[SEQ_SMEM_WORDS];
-    __shared__ __align__(16) int s_desc[VEC ? NT / 32 : 1][16];  // int16 path: per-warp trimmed lo[8] / hi[8] of the step's inputs
+    __shared__ uint32_t s_seq[VEC ? 1 : SEQ_SMEM_WORDS];
+    __shared__ uint2 s_seq2[VEC ? SEQ2_ENTRIES : 1];  // int16 path: pattern, text, reversed pattern, reversed text as overlapping word pairs
+    __shared__ __align__(16) int s_desc[VEC ? NT / 32 : 1][24];  // int16 path, per warp: trimmed lo[8] / hi[8] of the step's inputs, offsets[5] of its outputs
 
     const int tid = threadIdx.x;
     const AwPen pen = P.pen;
     int* const ws_i = P.ws + (size_t)blockIdx.x * P.ws_ints_per_cta;
     WS* const ws = reinterpret_cast<WS*>(ws_i);  // all wavefront offsets below are in WS elements
     const int W = P.W;
-    const int null_base = 2 * ring_n * NCOMP * W;               // int16 path: one all-NULL row after the rings
-    const int hist_base = null_base + (VEC ? W : 0);            // history arena starts after the rings
+    // int16 path: after the rings come one all-NULL row and the compact I/D rings (per direction e1+1 rows for each of
+    // I1/D1 and e2+1 rows for each of I2/D2): while the two wavefronts are far apart nobody reads an I/D row older than
+    // its extension distance, so those rows are overwritten while still in L2 instead of streaming through HBM
+    const int null_base = 2 * ring_n * NCOMP * W;
+    const int cmp_n1 = P.pen.e1 + 1, cmp_n2 = TWO ? P.pen.e2 + 1 : 0;
+    const int cmp_rows = 2 * cmp_n1 + 2 * cmp_n2;               // per direction
+    const int cmp_base = null_base + W;
+    const int hist_base = VEC ? cmp_base + 2 * cmp_rows * W : null_base;  // history arena starts after the rings
+    constexpr int VBW = VBLOCK_CHUNKS * CPT;  // diagonals per block of the per-block maxima
+    int* const blk_cta = VEC ? P.ws_blk + (size_t)blockIdx.x * 2 * ring_n * P.blk_cap * 2 : nullptr;
+    auto blk_of = [&](int d, int slot) -> int* { return blk_cta + (size_t)(d * ring_n + slot) * P.blk_cap * 2; };
     int* const hist_meta = P.ws_hist_meta + (size_t)blockIdx.x * (size_t)P.hist_max_scores * HIST_META_INTS;
     uint32_t* const pair_runs = P.ws_runs + (size_t)blockIdx.x * 2 * P.runs_cap;
     uint32_t* const leaf_runs = pair_runs + P.runs_cap;
@@ -828,7 +875,39 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         const uint32_t* pw = (BITS == 2) ? P.packed + qs.packed_off : reinterpret_cast<const uint32_t*>(P.ascii + qs.ascii_off);
         const uint32_t* tw = (BITS == 2) ? P.packed + ts.packed_off : reinterpret_cast<const uint32_t*>(P.ascii + ts.ascii_off);
         const int PLEN = (int)qs.len, TLEN = (int)ts.len;
-        {
+        const uint2 *pf2 = s_seq2, *tf2 = s_seq2, *pr2 = s_seq2, *tr2 = s_seq2;
+        bool seq_fits = true;
+        if constexpr (VEC) {
+            // entry i of a staged sequence = packed words (i, i+1); the reversed copy R[i] = S[len-1-i] is built from
+            // the same global words (bit-reverse a 16-symbol window, then swap the two bits of every symbol back)
+            const int np = PLEN / 16 + 2, ntt = TLEN / 16 + 2;
+            seq_fits = 2 * (np + ntt) <= SEQ2_ENTRIES;
+            uint2* s_pf = s_seq2;
+            uint2* s_tf = s_pf + np;
+            uint2* s_pr = s_tf + ntt;
+            uint2* s_tr = s_pr + np;
+            auto rev16 = [](const uint32_t* w, int len, int j) -> uint32_t {  // symbols 16j .. 16j+15 of the reversed sequence
+                const int a = len - 16 - 16 * j;                                 // first original symbol of the window (may be < 0: guard words)
+                const int idx = a >> 4;                                          // floor
+                const uint32_t x = __funnelshift_r(w[idx], w[idx + 1], (a & 15) * 2);
+                const uint32_t b = __brev(x);
+                return ((b >> 1) & 0x55555555u) | ((b & 0x55555555u) << 1);
+            };
+            if (seq_fits) {
+                for (int i = tid; i < np; i += NT) {
+                    s_pf[i] = make_uint2(pw[i], pw[i + 1]);
+                    s_pr[i] = make_uint2(rev16(pw, PLEN, i), rev16(pw, PLEN, i + 1));
+                }
+                for (int i = tid; i < ntt; i += NT) {
+                    s_tf[i] = make_uint2(tw[i], tw[i + 1]);
+                    s_tr[i] = make_uint2(rev16(tw, TLEN, i), rev16(tw, TLEN, i + 1));
+                }
+            }
+            pf2 = s_pf;
+            tf2 = s_tf;
+            pr2 = s_pr;
+            tr2 = s_tr;
+        } else {
             // stage both sequences (with 2 guard words either side) in shared memory when they fit
             constexpr int SPW = 32 / BITS;
             const int pwords = PLEN / SPW + 1, twords = TLEN / SPW + 1;
@@ -842,7 +921,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         const int koff = (min(PLEN + 1, W / 2) + RALIGN - 1) & ~(RALIGN - 1);  // diagonal k lives at index k + koff
         const int kmin_alloc = -koff, kmax_alloc = W - 1 - koff;
 
-        int status = ST_OK;
+        int status = seq_fits ? ST_OK : ST_FAIL_WORKSPACE;
         unsigned long long cyc[6] = {0, 0, 0, 0, 0, 0};
         long long tmark = clock64();
         auto lap = [&](int i) {
@@ -924,7 +1003,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             int width;    // history mode: allocated elements per component
         };
         long long hist_used = 0;  // history arena bump pointer (base case)
-        auto v_launch = [&](int d, int mbase, int s, int slot, int gwarp, int gnw, bool hist, const SeqView& sv, int k_end, int comp_end) -> VRange {
+        auto v_launch = [&](int d, int mbase, int s, int slot, int gwarp, int gnw, bool hist, bool full, const SeqView& sv, int k_end, int comp_end) -> VRange {
             constexpr int SH = (CPT == 8) ? 3 : (CPT == 4 ? 2 : 1);
             constexpr int MG = VMARGIN / CPT;
             const int lane = tid & 31;
@@ -939,7 +1018,13 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             else if (lane == IN_MO2) back = pen.o2 + pen.e2;
             else if (lane == IN_I2E) { comp = AW_COMP_I2; back = pen.e2; }
             else if (lane == IN_D2E) { comp = AW_COMP_D2; back = pen.e2; }
-            int ilo = VBIG, ihi = -VBIG, ioff = null_base + koff, iwlo = -VBIG, iwhi = VBIG;
+            int ilo = VBIG, ihi = -VBIG, ioff = null_base + koff, iwlo = -VBIG, iwhi = VBIG, pf_off = -1;
+            if (AW_PREFETCH_STEPS > 0 && (lane == IN_MO1 || (TWO && lane == IN_MO2)) && back > AW_PREFETCH_STEPS && s + AW_PREFETCH_STEPS - back >= 0) {
+                int sl = slot + AW_PREFETCH_STEPS - back;
+                if (sl < 0) sl += ring_n;
+                const SlotMeta& m = ring_meta[mbase + sl];
+                if (m.lo[AW_COMP_M] <= m.hi[AW_COMP_M]) pf_off = m.coff[AW_COMP_M];
+            }
             if (lane < (TWO ? 7 : 4) && s - back >= 0) {
                 int sl = slot - back;
                 if (sl < 0) sl += ring_n;
@@ -948,7 +1033,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 if (l <= h) {
                     ilo = l;
                     ihi = h;
-                    ioff = m.off + comp_idx(comp) * m.cstride;
+                    ioff = m.coff[comp];
                     iwlo = m.wlo;
                     iwhi = m.whi;
                 }
@@ -994,6 +1079,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             }
             const int c_lo = rg.lo >> SH, c_hi = rg.hi >> SH;
             int out_off, cstride, wlo, whi;
+            int my_coff = 0;  // lane c < 5: offset of output component c
             bool fail = false;
             if (!hist) {
                 fail = (rg.lo < kmin_alloc || rg.hi > kmax_alloc);
@@ -1001,6 +1087,14 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 cstride = W;
                 wlo = max((c_lo - MG) << SH, kmin_alloc);
                 whi = min(((c_hi + MG + 1) << SH) - 1, kmax_alloc);
+                fail = fail || ((c_hi - c_lo) / VBLOCK_CHUNKS + 1 > P.blk_cap);
+                my_coff = out_off + comp_idx(lane) * W;
+                if (!full && lane >= 1 && lane < 5) {
+                    const bool one = (lane == AW_COMP_I1 || lane == AW_COMP_D1);
+                    const int n = one ? cmp_n1 : cmp_n2;
+                    const int base = (lane == AW_COMP_I1) ? 0 : (lane == AW_COMP_D1) ? cmp_n1 : (lane == AW_COMP_I2) ? 2 * cmp_n1 : 2 * cmp_n1 + cmp_n2;
+                    my_coff = cmp_base + (d * cmp_rows + base + (n > 0 ? s % n : 0)) * W + koff;
+                }
             } else {
                 const int clo = (c_lo - MG) << SH;
                 rg.width = (c_hi - c_lo + 1 + 2 * MG) << SH;
@@ -1009,6 +1103,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 cstride = rg.width;
                 wlo = clo;
                 whi = clo + rg.width - 1;
+                my_coff = out_off + comp_idx(lane) * cstride;
             }
             if (fail) {
                 if (lead && lane == 0) r[RED_FAIL] = 1;
@@ -1024,19 +1119,26 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     }
                     mt.lo[lane] = pl;
                     mt.hi[lane] = ph;
+                    mt.coff[lane] = my_coff;
                 }
                 if (lane == 5) {
                     mt.off = out_off;
                     mt.cstride = cstride;
                     mt.wlo = wlo;
                     mt.whi = whi;
+                    mt.full = full ? 1 : 0;
+                    mt.bk0 = c_lo << SH;
+                    mt.nblk = (c_hi - c_lo) / VBLOCK_CHUNKS + 1;
                     r[RED_CLO] = rg.lo;
                     r[RED_CHI] = rg.hi;
                 }
             }
+            if (lane < 5) dsc[16 + lane] = my_coff;
+            __syncwarp();
             if constexpr (VEC)
-                wf_cells_v<BITS, TWO, CPT>(reinterpret_cast<short*>(ws), ioff, dsc, out_off, cstride, rg.lo, rg.hi, fast_lo, fast_hi, wlo, whi, sv.pw, sv.tw, sv.p0, sv.t0,
-                                           sv.plen, sv.tlen, sv.rev ? 1 : 0, k_end, comp_end, r, gwarp, gnw);
+                wf_cells_v<BITS, TWO, CPT>(reinterpret_cast<short*>(ws), ioff, dsc, dsc + 16, rg.lo, rg.hi, fast_lo, fast_hi, wlo, whi, reinterpret_cast<const uint2*>(sv.pw),
+                                           reinterpret_cast<const uint2*>(sv.tw), sv.p0, sv.t0, sv.plen, sv.tlen, k_end, comp_end, r, gwarp, gnw, pf_off,
+                                           hist ? nullptr : blk_of(d, slot));
             return rg;
         };
 //@region v_finish
@@ -1057,9 +1159,8 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             SlotMeta& mt = ring_meta[mbase + slot];
             if (oob) {  // exact wavefront_compute_trim_ends from the stored row (rare)
                 int out[5];
-                const int off = mt.off, cs = mt.cstride;
 #pragma unroll
-                for (int c = 0; c < 5; ++c) out[c] = off + comp_idx((TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M) * cs;
+                for (int c = 0; c < 5; ++c) out[c] = mt.coff[(TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M];
                 StepOut so;
                 wf_rescan<NT, TWO, WS>(ws, out, clo, chi, plen, tlen, r, so);
                 if (tid < 32) {
@@ -1110,11 +1211,13 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     for (int i = 0; i < CPT / 2; ++i) v[i] = NULL16X2;
                     if (kc == 0) {
                         int m = 0;
-                        if (cb == AW_COMP_M) m = extend_cell<BITS>(sv, 0, 0);
+                        if (cb == AW_COMP_M)
+                            m = lcp2(reinterpret_cast<const uint2*>(sv.pw), reinterpret_cast<const uint2*>(sv.tw), sv.p0, sv.t0, min(sv.plen, sv.tlen));
                         v[0] = (v[0] & 0xffff0000u) | ((uint32_t)m & 0xffffu);
                         r[RED_AKM] = (cb == AW_COMP_M) ? 2 * m : INT_MIN;
                         r[RED_AKALL] = 2 * m;
                         if (cb == ce && k_end == 0) r[RED_END] = m;
+                        if (!hist) *reinterpret_cast<int2*>(blk_of(d, 0)) = make_int2((cb == AW_COMP_M) ? 2 * m : INT_MIN, 2 * m);
                     }
                     if (kc >= clo && kc + CPT - 1 <= chi) st_vec<CPT>(row + kc, v);
                 }
@@ -1124,11 +1227,15 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     mt.lo[tid] = (tid == cb) ? 0 : 1;
                     mt.hi[tid] = 0;
                 }
+                if (tid < 5) mt.coff[tid] = out_off + comp_idx(tid) * cstride;
                 if (tid == 5) {
                     mt.off = out_off;
                     mt.cstride = cstride;
                     mt.wlo = clo;
                     mt.whi = chi;
+                    mt.full = 1;
+                    mt.bk0 = 0;
+                    mt.nblk = 1;
                 }
             }
             cta_sync<NT>();
@@ -1161,11 +1268,18 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             bp.score_f = bp.score_r = bp.k_f = bp.off_f = 0;
             bp.comp = AW_COMP_M;
 
+            bool force_full = false;  // int16 path: keep every I/D row in the full ring (second attempt, see below)
             if (!do_base) {
+            retry_breakpoint:
                 // =========== K6: wavefront_bialign_find_breakpoint ===========
                 SeqView svd[2];
-                svd[0] = SeqView{pw, tw, sp.pb, sp.tb, plen, tlen, false};
-                svd[1] = SeqView{pw, tw, sp.pe - 1, sp.te - 1, plen, tlen, true};
+                if constexpr (VEC) {
+                    svd[0] = SeqView{reinterpret_cast<const uint32_t*>(pf2), reinterpret_cast<const uint32_t*>(tf2), sp.pb, sp.tb, plen, tlen, false};
+                    svd[1] = SeqView{reinterpret_cast<const uint32_t*>(pr2), reinterpret_cast<const uint32_t*>(tr2), PLEN - sp.pe, TLEN - sp.te, plen, tlen, false};
+                } else {
+                    svd[0] = SeqView{pw, tw, sp.pb, sp.tb, plen, tlen, false};
+                    svd[1] = SeqView{pw, tw, sp.pe - 1, sp.te - 1, plen, tlen, true};
+                }
                 const int cbeg[2] = {sp.cb, sp.ce}, cend[2] = {sp.ce, sp.cb};
                 int cur_slot[2] = {0, 0};  // ring slot of the newest committed/computed score per direction
                 auto ring_off = [&](int d, int slot, int c) -> int { return ((d * ring_n + slot) * NCOMP + comp_idx(c)) * W + koff; };
@@ -1284,12 +1398,17 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     auto test_comp = [](int oi) -> int { return oi == 0 ? AW_COMP_D2 : oi == 1 ? AW_COMP_I2 : oi == 2 ? AW_COMP_D1 : oi == 3 ? AW_COMP_I1 : AW_COMP_M; };
                     auto credit_of = [&](int c) -> int { return (c == AW_COMP_M) ? 0 : ((c == AW_COMP_D1 || c == AW_COMP_I1) ? pen.o1 : pen.o2); };
                     // candidate tests (gate + range intersection + antidiagonal bound), kept in order, by warp 0
+                    // the scan ranges are cut along the block grid of A0's wavefront (int16 path; else a fixed grid)
+                    constexpr int OV_U = 8, OV_CH = VEC ? VBW : 32 * OV_U;  // diagonals per lane / per warp chunk of the scan
+                    static_assert(OV_CH <= 32 * OV_U, "a warp chunk must fit OV_U diagonals per lane");
+                    const int grid0 = VEC ? m0.bk0 : kmin_alloc;
                     if (tid < 32) {
-                        int ncand = 0;
+                        int ncand = 0, nchunk = 0;
                         const int ntests = min(scope, s1 + 1) * 5;
                         for (int base = 0; base < ntests; base += 32) {
                             const int t = base + tid;
                             bool ok = false;
+                            int klo = 0, khi = -1;
                             if (t < ntests) {
                                 const int i = t / 5, oi = t - 5 * i, c = test_comp(oi);
                                 const int si = s1 - i;
@@ -1297,6 +1416,8 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                                     const SlotMeta& m1 = ring_meta[d1 * ring_n + slot_back(cur_slot[d1], i)];
                                     const int lo0 = m0.lo[c], hi0 = m0.hi[c], lo1 = kinv - m1.hi[c], hi1 = kinv - m1.lo[c];
                                     ok = (s0 + si - credit_of(c) < bp_entry) && lo0 <= hi0 && m1.lo[c] <= m1.hi[c] && !(hi1 < lo0 || hi0 < lo1);
+                                    klo = max(lo0, lo1);
+                                    khi = min(hi0, hi1);
                                     if (ok) {
                                         const long long a0 = (c == AW_COMP_M) ? m0.akM : m0.akAll, a1 = (c == AW_COMP_M) ? m1.akM : m1.akAll;
                                         ok = a0 + a1 >= (long long)plen + tlen;  // necessary for off0 + off1 >= tlen
@@ -1304,50 +1425,80 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                                 }
                             }
                             const unsigned mask = __ballot_sync(0xffffffffu, ok);
+                            // inclusive warp scan of the candidates' chunk counts
+                            const int mych = ok ? (khi - grid0) / OV_CH - (klo - grid0) / OV_CH + 1 : 0;
+                            int inc = mych;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                                if (tid >= o) inc += v;
+                            }
                             if (ok) {
                                 const int pos = ncand + __popc(mask & ((1u << tid) - 1u));
                                 cand[pos] = t;
                                 hitk[pos] = INT_MAX;
+                                cklo[pos] = klo;
+                                ckhi[pos] = khi;
+                                cpre[pos] = nchunk + inc - mych;
                             }
                             ncand += __popc(mask);
+                            nchunk += __shfl_sync(0xffffffffu, inc, 31);
                         }
-                        if (tid == 0) s_ncand = ncand;
+                        if (tid == 0) {
+                            s_ncand = ncand;
+                            s_nchunk = nchunk;
+                            cpre[ncand] = nchunk;
+                        }
                     }
                     cta_sync<NT>();
                     const int ncand = s_ncand;
-                    for (int j = 0; j < ncand; ++j) {
-                        const int t = cand[j], i = t / 5, c = test_comp(t - 5 * i);
-                        const int sl1 = slot_back(cur_slot[d1], i);
-                        const SlotMeta& m1 = ring_meta[d1 * ring_n + sl1];
-                        const int lo_1 = kinv - m1.hi[c], hi_1 = kinv - m1.lo[c];
-                        const int max_lo = max(m0.lo[c], lo_1), min_hi = min(m0.hi[c], hi_1);
-                        const WS* p0 = ws + ring_off(d0, slot0, c);
-                        const WS* p1 = ws + ring_off(d1, sl1, c);
-                        int best = INT_MAX;
-                        // 4 diagonals per thread per round: the 8 loads are independent and issue together
-                        for (int kb0 = max_lo + tid; kb0 <= min_hi && best == INT_MAX; kb0 += 4 * NT) {
-                            int h0[4], h1[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int k0 = min(kb0 + j * NT, min_hi);  // clamped duplicates are re-tested harmlessly
-                                h0[j] = p0[k0];
-                                h1[j] = p1[kinv - k0];
+                    // first hit of every candidate: the scan ranges are cut into warp chunks of OV_CH diagonals and all
+                    // (candidate, chunk) pairs are spread over the warps, so the load latency is paid once, not once per candidate
+                    {
+                        const int nchunk = s_nchunk, lane = tid & 31;
+                        int j = 0;
+                        for (int fc = tid >> 5; fc < nchunk; fc += NT / 32) {
+                            while (cpre[j + 1] <= fc) ++j;
+                            const int b0 = (cklo[j] - grid0) / OV_CH + (fc - cpre[j]);
+                            const int max_lo = max(cklo[j], grid0 + b0 * OV_CH), min_hi = min(ckhi[j], grid0 + b0 * OV_CH + OV_CH - 1);
+                            const int kbase = max_lo;
+                            if (hitk[j] < kbase) continue;  // an earlier chunk already holds a hit
+                            const int t = cand[j], i = t / 5, c = test_comp(t - 5 * i);
+                            const int sl1 = slot_back(cur_slot[d1], i);
+                            const SlotMeta& m1 = ring_meta[d1 * ring_n + sl1];
+                            if constexpr (VEC) {
+                                // off0 + off1 >= tlen  <=>  (2 off0 - k0) + (2 off1 - k1) >= plen + tlen: bound both sides by their blocks' maxima
+                                const int sel = (c == AW_COMP_M) ? 0 : 1;
+                                const int* bl1 = blk_of(d1, sl1);
+                                const int a0 = blk_of(d0, slot0)[2 * b0 + sel];
+                                const int nb1 = m1.nblk - 1;
+                                const int b1a = min(max((kinv - min_hi - m1.bk0) / VBW, 0), nb1), b1b = min(max((kinv - max_lo - m1.bk0) / VBW, 0), nb1);
+                                const int a1 = max(bl1[2 * b1a + sel], bl1[2 * b1b + sel]);
+                                if ((long long)a0 + a1 < (long long)plen + tlen) continue;
                             }
+                            const WS* p0 = ws + (VEC ? m0.coff[c] : ring_off(d0, slot0, c));
+                            const WS* p1 = ws + (VEC ? m1.coff[c] : ring_off(d1, sl1, c)) + kinv;
+                            int h0[OV_U], h1[OV_U];
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int k0 = kb0 + j * NT;
-                                if (k0 > min_hi || best != INT_MAX) continue;
-                                if (h0[j] + h1[j] >= tlen) {
-                                    if (c != AW_COMP_M) {  // indel2indel: the forward cell must be in bounds
-                                        const int kk = (d0 == 0) ? k0 : kinv - k0, hh = (d0 == 0) ? h0[j] : h1[j];
-                                        if (hh - kk > plen || hh > tlen) continue;
-                                    }
-                                    best = k0;
+                            for (int u = 0; u < OV_U; ++u) {
+                                const int k0 = min(kbase + u * 32 + lane, min_hi);  // clamped duplicates are re-tested harmlessly
+                                h0[u] = p0[k0];
+                                h1[u] = p1[-k0];
+                            }
+                            int best = INT_MAX;
+#pragma unroll
+                            for (int u = OV_U - 1; u >= 0; --u) {
+                                const int k0 = kbase + u * 32 + lane;
+                                bool hit = (k0 <= min_hi) && (h0[u] + h1[u] >= tlen);
+                                if (hit && c != AW_COMP_M) {  // indel2indel: the forward cell must be in bounds
+                                    const int kk = (d0 == 0) ? k0 : kinv - k0, hh = (d0 == 0) ? h0[u] : h1[u];
+                                    hit = !(hh - kk > plen || hh > tlen);
                                 }
+                                if (hit) best = k0;
                             }
+                            best = __reduce_min_sync(0xffffffffu, best);
+                            if (lane == 0 && best != INT_MAX) atomicMin(&hitk[j], best);
                         }
-                        best = __reduce_min_sync(0xffffffffu, best);
-                        if ((tid & 31) == 0 && best != INT_MAX) atomicMin(&hitk[j], best);
                     }
                     cta_sync<NT>();
                     // replay the candidate tests in WFA2's order with the live breakpoint score
@@ -1359,7 +1510,8 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                         if (s0 + si - credit >= bp.score) continue;
                         const int sl1 = slot_back(cur_slot[d1], i);
                         const int k1 = kinv - k0;
-                        const int h0 = ws[ring_off(d0, slot0, c) + k0], h1 = ws[ring_off(d1, sl1, c) + k1];
+                        const int h0 = ws[(VEC ? m0.coff[c] : ring_off(d0, slot0, c)) + k0];
+                        const int h1 = ws[(VEC ? ring_meta[d1 * ring_n + sl1].coff[c] : ring_off(d1, sl1, c)) + k1];
                         if (d0 == 0) {
                             bp.score_f = s0;
                             bp.score_r = si;
@@ -1405,6 +1557,9 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 bool rev_pending = false;  // reverse wavefront score_r+1 already sits in slot next_slot(cur_slot[1])
                 const int max_antidiagonal = plen + tlen - 1;
                 bool rev_pending_done = false;  // END_REACHED flag of that speculative wavefront
+                // int16 path: I/D rows go to the compact rings until the wavefronts come close; the overlap phase needs the
+                // last `scope` rows of both directions in the full ring.  first_full = first score of the current run of full rows.
+                int first_full = 1;
                 lap(4);
                 // ---- phase 1: forward step s_f+1 and (speculative) reverse step s_r+1 share one barrier ----
                 while (!fb_end && status == ST_OK) {
@@ -1416,11 +1571,36 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                         // half of the warps advance the forward wavefront, the other half the reverse one
                         constexpr int HW = NT / 64;
                         const int warp = tid >> 5;
-                        if (warp < HW) v_launch(0, 0, score_f + 1, slot_f, warp, HW, false, svd[0], k_end, cend[0]);
-                        else v_launch(1, ring_n, score_r + 1, slot_r, warp - HW, HW, false, svd[1], k_end, cend[1]);
+                        // switch to the full ring 3 x scope expected steps before the wavefronts can touch
+                        const int reached = f_ak + r_ak;
+                        const int rate = reached / max(1, score_f) + 2;  // antidiagonals gained per step pair so far
+                        const bool full = !AW_COMPACT_ID_RINGS || force_full || (max_antidiagonal - reached <= 3 * scope * rate + 128);
+                        if (!full) first_full = INT_MAX;
+                        else if (first_full == INT_MAX) first_full = score_f + 1;
+                        {
+                            const int d = (warp < HW) ? 0 : 1;  // one call site for both directions (instruction-cache footprint)
+                            v_launch(d, d * ring_n, (d ? score_r : score_f) + 1, d ? slot_r : slot_f, d ? warp - HW : warp, HW, false, full, d ? svd[1] : svd[0], k_end,
+                                     d ? cend[1] : cend[0]);
+                        }
                         cta_sync<NT>();
-                        done = v_finish(0, 0, slot_f, plen, tlen, k_end, cend[0], akM_f);
-                        done_r = v_finish(1, ring_n, slot_r, plen, tlen, k_end, cend[1], akM_r);
+                        bool dn[2];
+                        int ak2[2];
+#pragma unroll 1
+                        for (int d = 0; d < 2; ++d) {
+                            int ak;
+                            const bool f = v_finish(d, d * ring_n, d ? slot_r : slot_f, plen, tlen, k_end, d ? cend[1] : cend[0], ak);
+                            if (d == 0) {
+                                dn[0] = f;
+                                ak2[0] = ak;
+                            } else {
+                                dn[1] = f;
+                                ak2[1] = ak;
+                            }
+                        }
+                        done = dn[0];
+                        done_r = dn[1];
+                        akM_f = ak2[0];
+                        akM_r = ak2[1];
                     } else {
                         const Range rf = launch_dir(0, score_f + 1, slot_f);
                         const Range rr = launch_dir(1, score_r + 1, slot_r);
@@ -1457,13 +1637,21 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     }
                 }
                 lap(0);
+                if constexpr (VEC) {
+                    if (!fb_end && status == ST_OK && first_full > max(1, score_r - (scope - 1))) {
+                        // the wavefronts met earlier than predicted: redo this breakpoint search with full rows only (rare)
+                        force_full = true;
+                        cta_sync<NT>();
+                        goto retry_breakpoint;
+                    }
+                }
                 // one committed step of direction d (phase 2): cells, barrier, finish
                 auto step_dir = [&](int d, int s) -> bool {
                     const int slot = next_slot(cur_slot[d]);
                     bool done;
                     if constexpr (VEC) {
                         int ak;
-                        v_launch(d, d * ring_n, s, slot, tid >> 5, NT / 32, false, d == 0 ? svd[0] : svd[1], k_end, d == 0 ? cend[0] : cend[1]);
+                        v_launch(d, d * ring_n, s, slot, tid >> 5, NT / 32, false, true, d == 0 ? svd[0] : svd[1], k_end, d == 0 ? cend[0] : cend[1]);
                         cta_sync<NT>();
                         done = v_finish(d, d * ring_n, slot, plen, tlen, k_end, d == 0 ? cend[0] : cend[1], ak);
                     } else {
@@ -1476,37 +1664,31 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     return done;
                 };
                 // ---- phase 2: advance until no better breakpoint is possible ----
+                // Half-steps: the direction that stepped last acts as aligner 0 of wavefront_bialign_overlap, then the other
+                // direction steps (one overlap / one step call site: instruction-cache footprint).
                 const int gap_opening = TWO ? pen.o2 : pen.o1;
+                int a0 = last_forward ? 0 : 1;
                 while (!fb_end && status == ST_OK) {
-                    if (last_forward) {
-                        const int min_r = (score_r > scope - 1) ? score_r - (scope - 1) : 0;
-                        if (score_f + min_r - gap_opening >= bp.score) break;
-                        overlap(0, 1, score_f, score_r);
-                        ++score_r;
-                        bool done;
-                        if (rev_pending) {  // computed speculatively in phase 1
-                            rev_pending = false;
-                            cur_slot[1] = next_slot(cur_slot[1]);
-                            done = rev_pending_done;
-                        } else {
-                            done = step_dir(1, score_r);
-                        }
-                        if (AW_BIALIGN_PHASE2_END_REACHED_RETURNS && done) {
-                            fb_end = true;
-                            break;
-                        }
-                        if (status != ST_OK) break;
+                    const int d0 = a0, d1 = 1 - a0;
+                    const int s0 = d0 ? score_r : score_f, s1 = d1 ? score_r : score_f;
+                    const int min1 = (s1 > scope - 1) ? s1 - (scope - 1) : 0;
+                    if (s0 + min1 - gap_opening >= bp.score) break;
+                    overlap(d0, d1, s0, s1);
+                    bool done;
+                    if (d1 == 1) ++score_r;
+                    else ++score_f;
+                    if (d1 == 1 && rev_pending) {  // computed speculatively in phase 1
+                        rev_pending = false;
+                        cur_slot[1] = next_slot(cur_slot[1]);
+                        done = rev_pending_done;
+                    } else {
+                        done = step_dir(d1, d1 ? score_r : score_f);
                     }
-                    const int min_f = (score_f > scope - 1) ? score_f - (scope - 1) : 0;
-                    if (min_f + score_r - gap_opening >= bp.score) break;
-                    overlap(1, 0, score_r, score_f);
-                    ++score_f;
-                    const bool done = step_dir(0, score_f);
                     if (AW_BIALIGN_PHASE2_END_REACHED_RETURNS && done) {
                         fb_end = true;
                         break;
                     }
-                    last_forward = true;
+                    a0 = d1;
                 }
                 lap(1);
                 if (status != ST_OK) break;
@@ -1534,7 +1716,8 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             {
                 ++w_base;
                 lap(5);
-                const SeqView sv = SeqView{pw, tw, sp.pb, sp.tb, plen, tlen, false};
+                const SeqView sv = VEC ? SeqView{reinterpret_cast<const uint32_t*>(pf2), reinterpret_cast<const uint32_t*>(tf2), sp.pb, sp.tb, plen, tlen, false}
+                                       : SeqView{pw, tw, sp.pb, sp.tb, plen, tlen, false};
                 hist_used = 0;
                 // component block of a history wavefront: element (c,k) at ws[hist_off(off,width,clo,c) + k]
                 auto hist_off = [&](int off, int width, int clo, int c) -> int { return hist_base + off + comp_idx(c) * width - clo; };
@@ -1569,7 +1752,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                             status = ST_FAIL_WORKSPACE;
                             break;
                         }
-                        const VRange rg = v_launch(0, 0, score, slot, tid >> 5, NT / 32, true, sv, k_end, sp.ce);
+                        const VRange rg = v_launch(0, 0, score, slot, tid >> 5, NT / 32, true, true, sv, k_end, sp.ce);
                         hist_used += (long long)NCOMP * rg.width;
                         cta_sync<NT>();
                         done = v_finish(0, 0, slot, plen, tlen, k_end, sp.ce, ak);
