@@ -237,7 +237,7 @@ extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
     std::string k(key);
     if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
     else if (k == "threads_per_cta") {
-        if (value != 0 && value != 32 && value != 64 && value != 128 && value != 256) return AW_EINVAL;
+        if (value != 0 && value != 32 && value != 128 && value != 256) return AW_EINVAL;
         c->threads_per_cta = (int)value;
     } else if (k == "max_wavefront_width") c->max_w = value;
     else if (k == "hist_mb") c->hist_mb = value;
@@ -652,16 +652,9 @@ cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bo
     AW_CASE(256, 8, true, short, true)
     AW_CASE(256, 8, false, short, true)
     AW_CASE(128, 2, false, short, true)
-    AW_CASE(128, 8, true, short, true)
-    AW_CASE(128, 8, false, short, true)
-    AW_CASE(128, 2, true, int, false)
-    AW_CASE(128, 2, false, int, false)
-    AW_CASE(128, 8, true, int, false)
-    AW_CASE(128, 8, false, int, false)
 #endif
     AW_CASE(256, 2, true, short, true)
     AW_CASE(128, 2, true, short, true)
-    AW_CASE(64, 2, true, short, true)
 #undef AW_CASE
     return cudaErrorInvalidValue;
 }
@@ -671,7 +664,11 @@ cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bo
 int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, uint64_t max_t, int attempt, LaunchCfg* cfg) {
     const int ncomp = pen.two_piece ? 5 : 3;
     const uint64_t maxlen = std::max(max_p, max_t);
-    int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : 256);
+    // int16 storage: every offset (incl. out-of-bounds I/D drift, <= 2*tlen+plen) must stay below 32000
+    const bool fits16 = c->ws16 && (2 * max_t + max_p < 32000) && (2 * max_p + max_t < 32000);
+    // pairs up to 1 kb: one warp per pair; int16-sized pairs on 2-bit sequences: 128 threads (2 warps per direction,
+    // 4 CTAs per SM measured best on C2); everything else: 256 threads
+    int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : ((fits16 && c->all_clean) ? 128 : 256));
     int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : AW_CTAS_PER_SM(nt));
     uint64_t full_w = (max_p + max_t + 3 + 16 + 15) & ~15ull;  // rows are 16-element aligned (vectorised int16 loop)
     uint64_t W = full_w;
@@ -681,8 +678,8 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     for (int a = 0; a < attempt; ++a) hist_ints *= 8;
     int hist_max_scores = attempt == 0 ? (nt == 32 ? 1024 : 4096) : (attempt == 1 ? 32768 : 262144);
     uint64_t runs_cap = max_p + max_t + 4;
-    // int16 storage: every offset (incl. out-of-bounds I/D drift, <= 2*tlen+plen) must stay below 32000
-    const bool ws16 = c->ws16 && nt >= 64 && (2 * max_t + max_p < 32000) && (2 * max_p + max_t < 32000);
+    if (nt == 128 && !(fits16 && c->all_clean)) nt = 256;  // the 128-thread kernels exist for the int16 2-bit path only
+    const bool ws16 = fits16 && nt >= 64;
     const uint64_t epi = ws16 ? 2 : 1;  // elements per int
     // + the all-NULL row and the compact I/D rings of the int16 path (aw_wfa.cuh: null_base, cmp_base)
     const uint64_t cmp_rows = 2ull * (2 * (pen.e1 + 1) + (pen.two_piece ? 2 * (pen.e2 + 1) : 0));

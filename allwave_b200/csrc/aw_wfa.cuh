@@ -28,6 +28,9 @@ namespace awk {
 // alone overflow L2), and the extra addressing costs ~10 %, so it is off by default.
 #define AW_COMPACT_ID_RINGS 0
 #endif
+#ifndef AW_L1_PREFETCH
+#define AW_L1_PREFETCH 0  // int16 path: after a step, prefetch into L1 the row chunks the next step will read (measured: -3 % on C2, off)
+#endif
 #ifndef AW_REGS
 #define AW_REGS 128  // register budget per thread of the CTA-per-pair kernels: resident CTAs per SM = 65536 / (NT * AW_REGS)
 #endif
@@ -621,6 +624,13 @@ __device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, cons
             for (int i = 0; i < VW; ++i) vM[i] = __byte_perm((uint32_t)mm[2 * i], (uint32_t)mm[2 * i + 1], 0x5410);
             st_vec<CPT>(pk + o_m, vM);
         }
+        if (AW_L1_PREFETCH && own) {  // the next step reads the same diagonals of these rows: pull their lines into L1 now
+#pragma unroll
+            for (int i = 0; i < (TWO ? 7 : 4); ++i) {
+                const int o = dsc[24 + i];
+                if (o >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ws + kc + o));
+            }
+        }
         if (blk != nullptr) {
             akM_b = __reduce_max_sync(0xffffffffu, akM_b);
             akAll_b = __reduce_max_sync(0xffffffffu, akAll_b);
@@ -820,7 +830,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     __shared__ unsigned long long s_text_off, s_bytes_off;
     __shared__ uint32_t s_seq[VEC ? 1 : SEQ_SMEM_WORDS];
     __shared__ uint2 s_seq2[VEC ? SEQ2_ENTRIES : 1];  // int16 path: pattern, text, reversed pattern, reversed text as overlapping word pairs
-    __shared__ __align__(16) int s_desc[VEC ? NT / 32 : 1][24];  // int16 path, per warp: trimmed lo[8] / hi[8] of the step's inputs, offsets[5] of its outputs
+    __shared__ __align__(16) int s_desc[VEC ? NT / 32 : 1][32];  // ... and [24..30] the rows the next step will read (L1 prefetch)  // int16 path, per warp: trimmed lo[8] / hi[8] of the step's inputs, offsets[5] of its outputs
 
     const int tid = threadIdx.x;
     const AwPen pen = P.pen;
@@ -1134,6 +1144,21 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 }
             }
             if (lane < 5) dsc[16 + lane] = my_coff;
+            if (AW_L1_PREFETCH) {
+                // inputs of wavefront s+1: the row being written now (extension distance 1) or an older row
+                int pfo = __shfl_sync(0xffffffffu, my_coff, comp);
+                if (back != 1) {
+                    pfo = -1;
+                    if (lane < (TWO ? 7 : 4) && s + 1 - back >= 0) {
+                        int sl = slot + 1 - back;
+                        if (sl < 0) sl += ring_n;
+                        const SlotMeta& m = ring_meta[mbase + sl];
+                        if (m.lo[comp] <= m.hi[comp]) pfo = m.coff[comp];
+                    }
+                }
+                if (lane >= (TWO ? 7 : 4)) pfo = -1;
+                if (lane < 8) dsc[24 + lane] = pfo;
+            }
             __syncwarp();
             if constexpr (VEC)
                 wf_cells_v<BITS, TWO, CPT>(reinterpret_cast<short*>(ws), ioff, dsc, dsc + 16, rg.lo, rg.hi, fast_lo, fast_hi, wlo, whi, reinterpret_cast<const uint2*>(sv.pw),
