@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -28,25 +29,86 @@ void aw_set_error(const char* fmt, ...) {
 
 namespace {
 
+// ---- caching allocator: cudaMalloc / cudaFree / cudaHostAlloc synchronise the device and cost 0.1 - 100 ms each, and
+// the host-facing calls (aw_load_sequences, aw_align_pairs) need the same few buffers on every call.  Released buffers
+// are parked per device (device memory) or globally (pinned host memory) and handed out again best-fit.
+struct BufCache {
+    std::mutex mu;
+    std::multimap<size_t, void*> free_dev[64];
+    std::multimap<size_t, void*> free_pin;
+    size_t parked_dev[64] = {0}, parked_pin = 0;
+    static constexpr size_t kMaxParkedDev = 24ull << 30, kMaxParkedPin = 2ull << 30;
+    static size_t round_up(size_t b) {
+        const size_t g = b >= (1u << 20) ? (2u << 20) : (64u << 10);
+        return ((b ? b : 1) + g - 1) / g * g;
+    }
+    void* take(std::multimap<size_t, void*>& m, size_t& parked, size_t want, size_t* got) {
+        auto it = m.lower_bound(want);
+        if (it == m.end() || it->first > 2 * want + (4u << 20)) return nullptr;
+        void* p = it->second;
+        *got = it->first;
+        parked -= it->first;
+        m.erase(it);
+        return p;
+    }
+    void trim_dev(int dev) {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : free_dev[dev]) cudaFree(kv.second);
+        free_dev[dev].clear();
+        parked_dev[dev] = 0;
+    }
+    void trim_pin() {
+        std::lock_guard<std::mutex> g(mu);
+        for (auto& kv : free_pin) cudaFreeHost(kv.second);
+        free_pin.clear();
+        parked_pin = 0;
+    }
+};
+static BufCache g_cache;
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    int dev = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return AW_OK;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        release();
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+        const size_t want = BufCache::round_up(bytes);
+        {
+            std::lock_guard<std::mutex> g(g_cache.mu);
+            size_t got = 0;
+            if (void* q = g_cache.take(g_cache.free_dev[dev], g_cache.parked_dev[dev], want, &got)) {
+                p = q;
+                cap = got;
+                return AW_OK;
+            }
+        }
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {  // give the parked buffers back to the driver and try once more
+            cudaGetLastError();
+            g_cache.trim_dev(dev);
+            e = cudaMalloc(&p, want);
+        }
         if (e != cudaSuccess) {
-            aw_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+            p = nullptr;
+            aw_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
             cudaGetLastError();
             return AW_ENOMEM;
         }
-        cap = bytes;
+        cap = want;
         return AW_OK;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            std::lock_guard<std::mutex> g(g_cache.mu);
+            if (g_cache.parked_dev[dev] + cap <= BufCache::kMaxParkedDev) {
+                g_cache.free_dev[dev].emplace(cap, p);
+                g_cache.parked_dev[dev] += cap;
+            } else {
+                cudaFree(p);
+            }
+        }
         p = nullptr;
         cap = 0;
     }
@@ -58,12 +120,20 @@ struct PinBuf {
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return AW_OK;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 4 + 4096;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        release();
+        const size_t want = BufCache::round_up(bytes + bytes / 4 + 4096);
+        {
+            std::lock_guard<std::mutex> g(g_cache.mu);
+            size_t got = 0;
+            if (void* q = g_cache.take(g_cache.free_pin, g_cache.parked_pin, want, &got)) {
+                p = q;
+                cap = got;
+                return AW_OK;
+            }
+        }
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
         if (e != cudaSuccess) {
+            p = nullptr;
             aw_set_error("cudaHostAlloc(%zu) failed: %s", want, cudaGetErrorString(e));
             cudaGetLastError();
             return AW_ENOMEM;
@@ -72,7 +142,15 @@ struct PinBuf {
         return AW_OK;
     }
     void release() {
-        if (p) cudaFreeHost(p);
+        if (p) {
+            std::lock_guard<std::mutex> g(g_cache.mu);
+            if (g_cache.parked_pin + cap <= BufCache::kMaxParkedPin) {
+                g_cache.free_pin.emplace(cap, p);
+                g_cache.parked_pin += cap;
+            } else {
+                cudaFreeHost(p);
+            }
+        }
         p = nullptr;
         cap = 0;
     }
@@ -695,7 +773,12 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     uint64_t per_cta = ws_ints * 4 + (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 + runs_cap * 8;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return AW_ECUDA;
-    uint64_t budget = (uint64_t)((double)(free_b + c->ws_main.cap + c->ws_hist_meta.cap + c->ws_runs.cap) * 0.85);
+    size_t parked = 0;
+    {
+        std::lock_guard<std::mutex> g(g_cache.mu);
+        parked = g_cache.parked_dev[c->device >= 0 && c->device < 64 ? c->device : 0];
+    }
+    uint64_t budget = (uint64_t)((double)(free_b + parked + c->ws_main.cap + c->ws_hist_meta.cap + c->ws_runs.cap) * 0.85);
     uint64_t grid = (uint64_t)c->sm_count * per_sm;
     grid = std::min<uint64_t>(grid, std::max<uint64_t>(1, npairs));
     while (grid > 1 && grid * per_cta > budget) grid = grid / 2;

@@ -241,8 +241,12 @@ def main():
     ia = (C.c_char_p * n)(*[i.encode() for i in ids])
 
     def e2e_step():
+        t_a = time.perf_counter()
         aw._cabi.check(L.aw_load_sequences(ctx2._h, n, sa, la, ia), "aw_load_sequences")
+        t_b = time.perf_counter()
         aw._cabi.check(L.aw_align_pairs(ctx2._h, C.byref(params), aw.AW_ORIENT_MASH, arr, len(pairs), 0, cb, None), "aw_align_pairs")
+        if os.environ.get("AW_BENCH_TRACE"):
+            print(f"[e2e] load {1e3 * (t_b - t_a):.1f} ms, align_pairs {1e3 * (time.perf_counter() - t_b):.1f} ms", file=sys.stderr)
 
     e2e_step()  # warm-up (allocations)
     acc.update(paf_bytes=0, n=0)
@@ -285,7 +289,7 @@ def main():
             pass
         line = {
             "metric": "aligned pairs/s", "value": value, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "nseq": args.nseq, "partition": f"host LPT over {world} GPUs, no collective",
                        "l2": "per-launch working set (wavefront rings + history, >10 GB) exceeds the 126 MB L2; no explicit flush"},
             "gbp_per_s": block_total * args.steps / (ms_max / 1e3) / 1e9,
