@@ -191,7 +191,7 @@ struct aw_ctx {
     bool have_stranded = false;
     std::map<std::pair<int, uint32_t>, SketchSet*> canonical;
     // grow-only per-launch workspace (one launch in flight per context)
-    DevBuf ws_main, ws_hist_meta, ws_runs, ws_blk;
+    DevBuf ws_main, ws_hist_meta, ws_runs, ws_blk, ws_seq2;
 };
 
 struct aw_batch {
@@ -305,6 +305,7 @@ extern "C" void aw_destroy(aw_ctx* c) {
     c->ws_main.release();
     c->ws_hist_meta.release();
     c->ws_blk.release();
+    c->ws_seq2.release();
     c->ws_runs.release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -699,6 +700,7 @@ struct LaunchCfg {
     bool ws16;
     int hist_max_scores;
     int blk_cap;
+    unsigned long long seq2_cap;
 };
 
 template <int NT, int BITS, bool TWO, class WS>
@@ -750,7 +752,6 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : AW_CTAS_PER_SM(nt));
     uint64_t full_w = (max_p + max_t + 3 + 16 + 15) & ~15ull;  // rows are 16-element aligned (vectorised int16 loop)
     uint64_t W = full_w;
-    if (attempt == 0 && W > (uint64_t)c->max_w) W = std::max<uint64_t>(32, (uint64_t)c->max_w & ~15ull);
     uint64_t hist_ints = (uint64_t)c->hist_mb * (1u << 20) / 4;
     if (nt == 32 && attempt == 0) hist_ints = std::min<uint64_t>(hist_ints, 1u << 18);
     for (int a = 0; a < attempt; ++a) hist_ints *= 8;
@@ -761,6 +762,27 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     const uint64_t epi = ws16 ? 2 : 1;  // elements per int
     // + the all-NULL row and the compact I/D rings of the int16 path (aw_wfa.cuh: null_base, cmp_base)
     const uint64_t cmp_rows = 2ull * (2 * (pen.e1 + 1) + (pen.two_piece ? 2 * (pen.e2 + 1) : 0));
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return AW_ECUDA;
+    size_t parked = 0;
+    {
+        std::lock_guard<std::mutex> g(g_cache.mu);
+        parked = g_cache.parked_dev[c->device >= 0 && c->device < 64 ? c->device : 0];
+    }
+    const uint64_t budget = (uint64_t)((double)(free_b + parked + c->ws_main.cap + c->ws_hist_meta.cap + c->ws_runs.cap + c->ws_blk.cap + c->ws_seq2.cap) * 0.85);
+    const uint64_t want_grid = std::min<uint64_t>((uint64_t)c->sm_count * per_sm, std::max<uint64_t>(1, npairs));
+    if (attempt == 0) {
+        // first try: as many diagonals per wavefront as let every resident CTA have its own workspace (a wavefront
+        // is at most 2*score+1 wide, far below plen+tlen for similar sequences); pairs that need more report
+        // AW_EWORKSPACE and are re-run with the full width on fewer CTAs
+        const uint64_t rows = 2ull * (pen.scope + 1) * ncomp + 1 + cmp_rows;
+        const uint64_t fixed = hist_ints * 4 + (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 + runs_cap * 8 + (full_w / 16 + 8) * 16;
+        const uint64_t share = budget / want_grid;
+        uint64_t w_fit = share > fixed ? (share - fixed) / (rows * (ws16 ? 2 : 4)) : 0;
+        w_fit = std::max<uint64_t>(w_fit & ~15ull, std::min<uint64_t>(full_w, 65536));
+        W = std::min(W, w_fit);
+        if (W > (uint64_t)c->max_w) W = std::max<uint64_t>(32, (uint64_t)c->max_w & ~15ull);
+    }
     uint64_t ring_ints = ((2ull * (pen.scope + 1) * ncomp + 1 + cmp_rows) * W + epi - 1) / epi;
     if (ring_ints >= 0x7f000000ull) {
         aw_set_error("wavefront ring of %llu ints per CTA exceeds the 32-bit workspace index", (unsigned long long)ring_ints);
@@ -770,17 +792,8 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     hist_ints &= ~7ull;
     ring_ints = (ring_ints + 7) & ~7ull;
     uint64_t ws_ints = ring_ints + hist_ints;
-    uint64_t per_cta = ws_ints * 4 + (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 + runs_cap * 8;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return AW_ECUDA;
-    size_t parked = 0;
-    {
-        std::lock_guard<std::mutex> g(g_cache.mu);
-        parked = g_cache.parked_dev[c->device >= 0 && c->device < 64 ? c->device : 0];
-    }
-    uint64_t budget = (uint64_t)((double)(free_b + parked + c->ws_main.cap + c->ws_hist_meta.cap + c->ws_runs.cap) * 0.85);
-    uint64_t grid = (uint64_t)c->sm_count * per_sm;
-    grid = std::min<uint64_t>(grid, std::max<uint64_t>(1, npairs));
+    uint64_t per_cta = ws_ints * 4 + (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 + runs_cap * 8 + (full_w / 16 + 8) * 16;
+    uint64_t grid = want_grid;
     while (grid > 1 && grid * per_cta > budget) grid = grid / 2;
     if (grid * per_cta > budget) {
         aw_set_error("device workspace for one pair (%llu MB) does not fit in free memory", (unsigned long long)(per_cta >> 20));
@@ -794,10 +807,13 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     cfg->ws16 = ws16;
     cfg->runs_cap = runs_cap;
     cfg->hist_max_scores = hist_max_scores;
-    cfg->blk_cap = (int)(W / (awk::VBLOCK_CHUNKS * 4) + 2);  // blocks of >= 30 x 4 diagonals (AW_CPT >= 4)
+    cfg->blk_cap = (int)(W / (awk::VBLOCK_CHUNKS * 4) + 2);  // blocks of >= 30 x 4 diagonals
+    // pairs too long for the shared-memory staging keep their 4 word-pair arrays (pattern, text, both reversed) per CTA
+    cfg->seq2_cap = (!ws16 && nt >= 64 && c->all_clean) ? 2 * ((max_p / 16 + 2) + (max_t / 16 + 2)) : 0;
     int rc;
     if ((rc = c->ws_main.ensure(grid * ws_ints * 4)) ||
         (rc = c->ws_blk.ensure(grid * 2ull * (pen.scope + 1) * (uint64_t)cfg->blk_cap * 2 * 4)) ||
+        (rc = c->ws_seq2.ensure(grid * cfg->seq2_cap * 8 + 16)) ||
         (rc = c->ws_hist_meta.ensure(grid * (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4)) || (rc = c->ws_runs.ensure(grid * runs_cap * 8)))
         return rc;
     return AW_OK;
@@ -821,6 +837,8 @@ void fill_params(aw_ctx* c, aw_batch* b, const AwPen& pen, const LaunchCfg& cfg,
     P->ws_hist_meta = c->ws_hist_meta.as<int>();
     P->ws_blk = c->ws_blk.as<int>();
     P->blk_cap = cfg.blk_cap;
+    P->ws_seq2 = c->ws_seq2.as<uint2>();
+    P->seq2_cap = cfg.seq2_cap;
     P->hist_max_scores = cfg.hist_max_scores;
     P->ws_runs = c->ws_runs.as<uint32_t>();
     P->runs_cap = cfg.runs_cap;

@@ -16,9 +16,6 @@
 namespace awk {
 
 #define AW_KFLAG_COUNT_ONLY 0x100u  // internal: statistics only (orientation passes), no text output
-#ifndef AW_CPT
-#define AW_CPT 8
-#endif
 #ifndef AW_PREFETCH_STEPS
 #define AW_PREFETCH_STEPS 0  // int16 path: L2 prefetch distance (score steps) for the old M rows; 0 = off (measured: no gain on C2)
 #endif
@@ -100,6 +97,8 @@ struct KParams {
     unsigned long long ws_ints_per_cta;
     int W;                   // allocated diagonals per ring wavefront
     int hist_ints;           // history arena size (ints)
+    uint2* ws_seq2;          // chunked path, pairs too long for shared memory: [cta][seq2_cap] staged sequence word pairs
+    unsigned long long seq2_cap;
     int* ws_blk;             // int16 path: [cta][2 directions][scope+1 slots][blk_cap][2] per-block (akM, akAll) maxima
     int blk_cap;
     int* ws_hist_meta;       // [cta][hist_max_scores][HIST_META_INTS]
@@ -413,50 +412,73 @@ constexpr int VMARGIN = 48;
 constexpr int VBLOCK_CHUNKS = 30;  // = chunks owned per warp iteration
 constexpr int VBIG = 1 << 28;
 
-template <int CPT>
-__device__ __forceinline__ void ld_vec(const short* __restrict__ p, uint32_t (&v)[CPT / 2]) {
-    if constexpr (CPT == 8) {
-        const uint4 t = *reinterpret_cast<const uint4*>(p);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else if constexpr (CPT == 4) {
-        const uint2 t = *reinterpret_cast<const uint2*>(p);
-        v[0] = t.x; v[1] = t.y;
-    } else {
-        v[0] = *reinterpret_cast<const uint32_t*>(p);
-    }
+// Element traits of the chunked loop: int16 rows hold two cells per 32-bit word (packed VIMNMX / VIADD.16x2
+// arithmetic), int32 rows one.  A chunk is always 16 bytes: 8 int16 cells or 4 int32 cells.
+template <class WS>
+struct VecT;
+template <>
+struct VecT<short> {
+    static constexpr int CPW = 2;  // cells per word
+    static constexpr uint32_t NULLW = NULL16X2;
+    static constexpr int NULLV = NULL16;
+    static __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+    static __device__ __forceinline__ uint32_t inc(uint32_t a) { return a + 0x00010001u; }  // nulls never hold 0xffff: no carry between halves
+    static __device__ __forceinline__ uint32_t mstep(uint32_t mx, uint32_t i1) { return __viaddmax_s16x2(mx, 0x00010001u, i1); }  // max(mx + 1, i1)
+    static __device__ __forceinline__ uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }
+    // words of a row shifted by one cell: `lo` supplies the cell that moves in from the left / `hi` from the right
+    static __device__ __forceinline__ uint32_t shl1(uint32_t lo, uint32_t cur) { return __byte_perm(lo, cur, 0x5432); }
+    static __device__ __forceinline__ uint32_t shr1(uint32_t cur, uint32_t hi) { return __byte_perm(cur, hi, 0x5432); }
+    static __device__ __forceinline__ int get(const uint32_t* v, int j) { return (j & 1) ? (int)v[j >> 1] >> 16 : (int)(short)(v[j >> 1] & 0xffffu); }
+};
+template <>
+struct VecT<int> {
+    static constexpr int CPW = 1;
+    static constexpr uint32_t NULLW = (uint32_t)AW_NULLV;
+    static constexpr int NULLV = AW_NULLV;
+    static __device__ __forceinline__ uint32_t vmax(uint32_t a, uint32_t b) { return (uint32_t)max((int)a, (int)b); }
+    static __device__ __forceinline__ uint32_t inc(uint32_t a) { return a + 1u; }
+    static __device__ __forceinline__ uint32_t mstep(uint32_t mx, uint32_t i1) { return (uint32_t)max((int)mx + 1, (int)i1); }
+    static __device__ __forceinline__ uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return (uint32_t)max((int)a, max((int)b, (int)c)); }
+    static __device__ __forceinline__ uint32_t shl1(uint32_t lo, uint32_t) { return lo; }
+    static __device__ __forceinline__ uint32_t shr1(uint32_t, uint32_t hi) { return hi; }
+    static __device__ __forceinline__ int get(const uint32_t* v, int j) { return (int)v[j]; }
+};
+
+template <class WS>
+__device__ __forceinline__ void ld_vec(const WS* __restrict__ p, uint32_t (&v)[4]) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
-template <int CPT>
-__device__ __forceinline__ void st_vec(short* __restrict__ p, const uint32_t (&v)[CPT / 2]) {
-    if constexpr (CPT == 8) {
-        *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
-    } else if constexpr (CPT == 4) {
-        *reinterpret_cast<uint2*>(p) = make_uint2(v[0], v[1]);
-    } else {
-        *reinterpret_cast<uint32_t*>(p) = v[0];
-    }
+template <class WS>
+__device__ __forceinline__ void st_vec(WS* __restrict__ p, const uint32_t (&v)[4]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(v[0], v[1], v[2], v[3]);
 }
 // input row at diagonals [kc, kc+CPT): NULL outside the row's trimmed range [lo,hi]
-template <int CPT>
-__device__ __forceinline__ void load_row(const short* __restrict__ ws, int off, int lo, int hi, int kc, uint32_t (&v)[CPT / 2]) {
-    constexpr int VW = CPT / 2;
+template <class WS>
+__device__ __forceinline__ void load_row(const WS* __restrict__ ws, int off, int lo, int hi, int kc, uint32_t (&v)[4]) {
+    using T = VecT<WS>;
+    constexpr int CPT = 4 * T::CPW;
     const int k1 = kc + CPT - 1;
     if (k1 < lo || kc > hi) {
 #pragma unroll
-        for (int i = 0; i < VW; ++i) v[i] = NULL16X2;
+        for (int i = 0; i < 4; ++i) v[i] = T::NULLW;
         return;
     }
-    ld_vec<CPT>(ws + off + kc, v);
+    ld_vec<WS>(ws + off + kc, v);
     if (kc < lo || k1 > hi) {
 #pragma unroll
-        for (int i = 0; i < VW; ++i) {
-            const int k = kc + 2 * i;
-            const bool a = (k >= lo && k <= hi), b = (k + 1 >= lo && k + 1 <= hi);
-            v[i] = (a ? (v[i] & 0xffffu) : (NULL16X2 & 0xffffu)) | (b ? (v[i] & 0xffff0000u) : (NULL16X2 & 0xffff0000u));
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (T::CPW == 2) {
+                const int k = kc + 2 * i;
+                const bool a = (k >= lo && k <= hi), b = (k + 1 >= lo && k + 1 <= hi);
+                v[i] = (a ? (v[i] & 0xffffu) : (T::NULLW & 0xffffu)) | (b ? (v[i] & 0xffff0000u) : (T::NULLW & 0xffff0000u));
+            } else {
+                const int k = kc + i;
+                if (k < lo || k > hi) v[i] = T::NULLW;
+            }
         }
     }
 }
-__device__ __forceinline__ int half_lo(uint32_t w) { return (int)(short)(w & 0xffffu); }
-__device__ __forceinline__ int half_hi(uint32_t w) { return (int)w >> 16; }
 
 // Called by the `gnw` warps of a group (gwarp = this warp's index in the group).
 //   in_off  : lane i < 7 holds the element offset (k = 0) of input i (IN_*); the NULL row when absent
@@ -464,11 +486,13 @@ __device__ __forceinline__ int half_hi(uint32_t w) { return (int)w >> 16; }
 //   ocoff   : shared memory, element offset (k = 0) of every output component (SlotMeta::coff)
 //   [lo,hi] : computed range; [fast_lo,fast_hi] : diagonals every input reads back unmasked
 //   [wlo,whi]: what this row must leave readable (computed chunks + NULL margin, clipped to the allocation)
-template <int BITS, bool TWO, int CPT>
-__device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, const int* dsc, const int* ocoff, int lo, int hi, int fast_lo, int fast_hi,
+template <int BITS, bool TWO, class WS>
+__device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const int* dsc, const int* ocoff, int lo, int hi, int fast_lo, int fast_hi,
                                         int wlo, int whi, const uint2* __restrict__ s_p2, const uint2* __restrict__ s_t2, int s_p0, int s_t0, int s_plen,
                                         int s_tlen, int k_end, int comp_end, int* red, int gwarp, int gnw, int pf_off, int* __restrict__ blk) {
-    static_assert(BITS == 2, "the int16 path reads 2-bit sequences");
+    static_assert(BITS == 2, "the chunked path reads 2-bit sequences");
+    using T = VecT<WS>;
+    constexpr int CPT = 4 * T::CPW;
     // pf_off: lanes IN_MO1 / IN_MO2 hold the element offset of the M row those inputs will be two steps from now
     // (or -1): rows that old have usually left L2, so their lines are requested now (prefetch.global.L2)
     int pf1 = -1, pf2 = -1;
@@ -476,8 +500,8 @@ __device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, cons
         pf1 = __shfl_sync(0xffffffffu, pf_off, IN_MO1);
         if (TWO) pf2 = __shfl_sync(0xffffffffu, pf_off, IN_MO2);
     }
-    constexpr int VW = CPT / 2;
-    constexpr int SH = (CPT == 8) ? 3 : (CPT == 4 ? 2 : 1);
+    constexpr int VW = 4;
+    constexpr int SH = (CPT == 8) ? 3 : 2;
     constexpr int OWN = VBLOCK_CHUNKS;  // chunks owned per warp iteration (lanes 1..30)
     const int lane = threadIdx.x & 31;
     const int o_mx = __shfl_sync(0xffffffffu, in_off, IN_MX), o_mo1 = __shfl_sync(0xffffffffu, in_off, IN_MO1);
@@ -502,42 +526,42 @@ __device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, cons
         uint32_t mx[VW], tI1[VW], tD1[VW], tI2[VW], tD2[VW];
         if (c > c_hi + 1) {  // neither owned nor a neighbour's halo
 #pragma unroll
-            for (int i = 0; i < VW; ++i) mx[i] = tI1[i] = tD1[i] = tI2[i] = tD2[i] = NULL16X2;
+            for (int i = 0; i < VW; ++i) mx[i] = tI1[i] = tD1[i] = tI2[i] = tD2[i] = T::NULLW;
         } else {
             uint32_t mo[VW], ie[VW], de[VW], mo2[VW], ie2[VW], de2[VW];
             if (fast) {
-                const short* pk = ws + kc;
+                const WS* pk = ws + kc;
                 if (AW_PREFETCH_STEPS > 0) {
                     if (pf1 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + pf1));
                     if (pf2 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + pf2));
                 }
-                ld_vec<CPT>(pk + o_mx, mx);
-                ld_vec<CPT>(pk + o_mo1, mo);
-                ld_vec<CPT>(pk + o_i1e, ie);
-                ld_vec<CPT>(pk + o_d1e, de);
+                ld_vec<WS>(pk + o_mx, mx);
+                ld_vec<WS>(pk + o_mo1, mo);
+                ld_vec<WS>(pk + o_i1e, ie);
+                ld_vec<WS>(pk + o_d1e, de);
                 if (TWO) {
-                    ld_vec<CPT>(pk + o_mo2, mo2);
-                    ld_vec<CPT>(pk + o_i2e, ie2);
-                    ld_vec<CPT>(pk + o_d2e, de2);
+                    ld_vec<WS>(pk + o_mo2, mo2);
+                    ld_vec<WS>(pk + o_i2e, ie2);
+                    ld_vec<WS>(pk + o_d2e, de2);
                 }
             } else {
-                load_row<CPT>(ws, o_mx, dsc[IN_MX], dsc[8 + IN_MX], kc, mx);
-                load_row<CPT>(ws, o_mo1, dsc[IN_MO1], dsc[8 + IN_MO1], kc, mo);
-                load_row<CPT>(ws, o_i1e, dsc[IN_I1E], dsc[8 + IN_I1E], kc, ie);
-                load_row<CPT>(ws, o_d1e, dsc[IN_D1E], dsc[8 + IN_D1E], kc, de);
+                load_row<WS>(ws, o_mx, dsc[IN_MX], dsc[8 + IN_MX], kc, mx);
+                load_row<WS>(ws, o_mo1, dsc[IN_MO1], dsc[8 + IN_MO1], kc, mo);
+                load_row<WS>(ws, o_i1e, dsc[IN_I1E], dsc[8 + IN_I1E], kc, ie);
+                load_row<WS>(ws, o_d1e, dsc[IN_D1E], dsc[8 + IN_D1E], kc, de);
                 if (TWO) {
-                    load_row<CPT>(ws, o_mo2, dsc[IN_MO2], dsc[8 + IN_MO2], kc, mo2);
-                    load_row<CPT>(ws, o_i2e, dsc[IN_I2E], dsc[8 + IN_I2E], kc, ie2);
-                    load_row<CPT>(ws, o_d2e, dsc[IN_D2E], dsc[8 + IN_D2E], kc, de2);
+                    load_row<WS>(ws, o_mo2, dsc[IN_MO2], dsc[8 + IN_MO2], kc, mo2);
+                    load_row<WS>(ws, o_i2e, dsc[IN_I2E], dsc[8 + IN_I2E], kc, ie2);
+                    load_row<WS>(ws, o_d2e, dsc[IN_D2E], dsc[8 + IN_D2E], kc, de2);
                 }
             }
 #pragma unroll
             for (int i = 0; i < VW; ++i) {
-                tI1[i] = __vmaxs2(mo[i], ie[i]);
-                tD1[i] = __vmaxs2(mo[i], de[i]);
+                tI1[i] = T::vmax(mo[i], ie[i]);
+                tD1[i] = T::vmax(mo[i], de[i]);
                 if (TWO) {
-                    tI2[i] = __vmaxs2(mo2[i], ie2[i]);
-                    tD2[i] = __vmaxs2(mo2[i], de2[i]);
+                    tI2[i] = T::vmax(mo2[i], ie2[i]);
+                    tD2[i] = T::vmax(mo2[i], de2[i]);
                 }
             }
         }
@@ -553,41 +577,41 @@ __device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, cons
             uint32_t vI1[VW], vD1[VW], vI2[VW], vD2[VW], vM[VW];
 #pragma unroll
             for (int i = 0; i < VW; ++i) {
-                vI1[i] = __byte_perm(i == 0 ? pI1 : tI1[i - 1], tI1[i], 0x5432) + 0x00010001u;  // nulls never hold 0xffff: no carry between halves
-                vD1[i] = __byte_perm(tD1[i], i == VW - 1 ? nD1 : tD1[i + 1], 0x5432);
-                uint32_t m = __viaddmax_s16x2(mx[i], 0x00010001u, vI1[i]);
+                vI1[i] = T::inc(T::shl1(i == 0 ? pI1 : tI1[i - 1], tI1[i]));
+                vD1[i] = T::shr1(tD1[i], i == VW - 1 ? nD1 : tD1[i + 1]);
+                uint32_t m = T::mstep(mx[i], vI1[i]);
                 if (TWO) {
-                    vI2[i] = __byte_perm(i == 0 ? pI2 : tI2[i - 1], tI2[i], 0x5432) + 0x00010001u;
-                    vD2[i] = __byte_perm(tD2[i], i == VW - 1 ? nD2 : tD2[i + 1], 0x5432);
-                    m = __vimax3_s16x2(m, vI2[i], vD1[i]);
-                    m = __vmaxs2(m, vD2[i]);
+                    vI2[i] = T::inc(T::shl1(i == 0 ? pI2 : tI2[i - 1], tI2[i]));
+                    vD2[i] = T::shr1(tD2[i], i == VW - 1 ? nD2 : tD2[i + 1]);
+                    m = T::vmax3(m, vI2[i], vD1[i]);
+                    m = T::vmax(m, vD2[i]);
                 } else {
-                    m = __vmaxs2(m, vD1[i]);
+                    m = T::vmax(m, vD1[i]);
                 }
                 vM[i] = m;
             }
-            short* pk = ws + kc;
-            st_vec<CPT>(pk + o_i1, vI1);
-            st_vec<CPT>(pk + o_d1, vD1);
+            WS* pk = ws + kc;
+            st_vec<WS>(pk + o_i1, vI1);
+            st_vec<WS>(pk + o_d1, vD1);
             if (TWO) {
-                st_vec<CPT>(pk + o_i2, vI2);
-                st_vec<CPT>(pk + o_d2, vD2);
+                st_vec<WS>(pk + o_i2, vI2);
+                st_vec<WS>(pk + o_d2, vD2);
             }
             if (comp_end != AW_COMP_M && k_end >= kc && k_end < kc + CPT) {
                 const int j = k_end - kc;
                 const uint32_t* src = (comp_end == AW_COMP_I1) ? vI1 : (comp_end == AW_COMP_D1) ? vD1 : (comp_end == AW_COMP_I2) ? vI2 : vD2;
-                uint32_t wsel = src[0];
+                int val = T::get(src, 0);
 #pragma unroll
-                for (int i = 1; i < VW; ++i)
-                    if ((j >> 1) == i) wsel = src[i];
-                red[RED_END] = (j & 1) ? half_hi(wsel) : half_lo(wsel);
+                for (int q = 1; q < CPT; ++q)
+                    if (j == q) val = T::get(src, q);
+                red[RED_END] = val;
             }
             int mm[CPT];
             unsigned more = 0;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int k = kc + j;
-                const int m = (j & 1) ? half_hi(vM[j >> 1]) : half_lo(vM[j >> 1]);
+                const int m = T::get(vM, j);
                 const int v = m - k;
                 const int maxlen = min(s_plen - v, s_tlen - m);
                 const bool valid = (m | v | maxlen) >= 0;  // 0 <= h <= tlen and 0 <= v <= plen
@@ -617,12 +641,15 @@ __device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, cons
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 if (mm[j] >= 0) akM_b = max(akM_b, 2 * mm[j] - (kc + j));
-                else mm[j] = NULL16;
+                else mm[j] = T::NULLV;
                 if (comp_end == AW_COMP_M && kc + j == k_end) red[RED_END] = mm[j];
             }
 #pragma unroll
-            for (int i = 0; i < VW; ++i) vM[i] = __byte_perm((uint32_t)mm[2 * i], (uint32_t)mm[2 * i + 1], 0x5410);
-            st_vec<CPT>(pk + o_m, vM);
+            for (int i = 0; i < VW; ++i) {
+                if constexpr (T::CPW == 2) vM[i] = __byte_perm((uint32_t)mm[2 * i], (uint32_t)mm[2 * i + 1], 0x5410);
+                else vM[i] = (uint32_t)mm[i];
+            }
+            st_vec<WS>(pk + o_m, vM);
         }
         if (AW_L1_PREFETCH && own) {  // the next step reads the same diagonals of these rows: pull their lines into L1 now
 #pragma unroll
@@ -645,13 +672,13 @@ __device__ __noinline__ void wf_cells_v(short* __restrict__ ws, int in_off, cons
         constexpr int NCOMP = TWO ? 5 : 3;
         uint32_t nullv[VW];
 #pragma unroll
-        for (int i = 0; i < VW; ++i) nullv[i] = NULL16X2;
+        for (int i = 0; i < VW; ++i) nullv[i] = T::NULLW;
         for (int i = lane; i < 2 * MG * NCOMP; i += 32) {
             const int ci = i / (2 * MG), j = i - ci * (2 * MG);
             const int comp = TWO ? ci : (ci == 2 ? AW_COMP_D1 : ci);
             const int c = (j < MG) ? (c_lo - MG + j) : (c_hi + 1 + (j - MG));
             const int kc = c << SH;
-            if (kc >= wlo && kc + CPT - 1 <= whi) st_vec<CPT>(ws + ocoff[comp] + kc, nullv);
+            if (kc >= wlo && kc + CPT - 1 <= whi) st_vec<WS>(ws + ocoff[comp] + kc, nullv);
         }
     }
     akM = __reduce_max_sync(0xffffffffu, akM);
@@ -808,9 +835,10 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
 template <int NT, int BITS, bool TWO, class WS>
 __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const KParams P) {
     constexpr int NCOMP = TWO ? 5 : 3;
-    constexpr bool VEC = (sizeof(WS) == 2) && (NT >= 64) && (BITS == 2);  // chunk-vectorised int16 cell loop
-    constexpr int CPT = AW_CPT;                            // diagonals per thread in that loop
-    constexpr int RALIGN = VEC ? 8 : 1;                    // row alignment (elements)
+    constexpr bool VEC = (NT >= 64) && (BITS == 2);        // chunked (16 bytes of cells per thread) wavefront loop
+    constexpr bool SEQ_SMEM = VEC && sizeof(WS) == 2;      // int16-sized pairs: sequences staged in shared memory
+    constexpr int CPT = 16 / sizeof(WS);                   // diagonals per thread in that loop: 8 int16 or 4 int32
+    constexpr int RALIGN = VEC ? CPT : 1;                  // row alignment (elements)
     extern __shared__ unsigned long long smem_raw[];
     const int scope = P.pen.scope;
     const int ring_n = scope + 1;  // one spare slot: the reverse step is computed speculatively
@@ -825,11 +853,13 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     __shared__ SubProblem stack[MAX_STACK];
     __shared__ unsigned s_next;
     __shared__ unsigned s_nruns;
-    __shared__ int s_ncand, s_nchunk;
+    __shared__ int s_ncand, s_nact, s_ov[4];  // s_ov: thresholds for M / other components, first and last diagonal of any candidate
+    constexpr int ACT_MAX = 256;
+    __shared__ int s_act[ACT_MAX];            // blocks of aligner 0's wavefront that can hold a meeting point
     __shared__ unsigned long long s_acc[8];
     __shared__ unsigned long long s_text_off, s_bytes_off;
     __shared__ uint32_t s_seq[VEC ? 1 : SEQ_SMEM_WORDS];
-    __shared__ uint2 s_seq2[VEC ? SEQ2_ENTRIES : 1];  // int16 path: pattern, text, reversed pattern, reversed text as overlapping word pairs
+    __shared__ uint2 s_seq2[SEQ_SMEM ? SEQ2_ENTRIES : 1];  // int16 path: pattern, text, reversed pattern, reversed text as overlapping word pairs
     __shared__ __align__(16) int s_desc[VEC ? NT / 32 : 1][32];  // ... and [24..30] the rows the next step will read (L1 prefetch)  // int16 path, per warp: trimmed lo[8] / hi[8] of the step's inputs, offsets[5] of its outputs
 
     const int tid = threadIdx.x;
@@ -854,8 +884,8 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
 
     for (int i = tid; i < 2 * 3 * NRED; i += NT) (&red[0][0][0])[i] = INT_MIN;
     if constexpr (VEC) {
-        const uint4 nv = make_uint4(NULL16X2, NULL16X2, NULL16X2, NULL16X2);
-        for (int i = tid * 8; i < W; i += NT * 8) *reinterpret_cast<uint4*>(ws + null_base + i) = nv;
+        const uint4 nv = make_uint4(VecT<WS>::NULLW, VecT<WS>::NULLW, VecT<WS>::NULLW, VecT<WS>::NULLW);
+        for (int i = tid * CPT; i < W; i += NT * CPT) *reinterpret_cast<uint4*>(ws + null_base + i) = nv;
     }
     int red_i = 0;  // rotating reduction buffer index (uniform)
     cta_sync<NT>();
@@ -891,8 +921,9 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             // entry i of a staged sequence = packed words (i, i+1); the reversed copy R[i] = S[len-1-i] is built from
             // the same global words (bit-reverse a 16-symbol window, then swap the two bits of every symbol back)
             const int np = PLEN / 16 + 2, ntt = TLEN / 16 + 2;
-            seq_fits = 2 * (np + ntt) <= SEQ2_ENTRIES;
-            uint2* s_pf = s_seq2;
+            seq_fits = SEQ_SMEM ? (2 * (np + ntt) <= SEQ2_ENTRIES) : ((unsigned long long)2 * (np + ntt) <= P.seq2_cap);
+            // longer pairs keep the four arrays in a per-CTA global scratch (L1/L2-cached 8-byte loads)
+            uint2* s_pf = SEQ_SMEM ? s_seq2 : P.ws_seq2 + (size_t)blockIdx.x * P.seq2_cap;
             uint2* s_tf = s_pf + np;
             uint2* s_pr = s_tf + ntt;
             uint2* s_tr = s_pr + np;
@@ -1014,7 +1045,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         };
         long long hist_used = 0;  // history arena bump pointer (base case)
         auto v_launch = [&](int d, int mbase, int s, int slot, int gwarp, int gnw, bool hist, bool full, const SeqView& sv, int k_end, int comp_end) -> VRange {
-            constexpr int SH = (CPT == 8) ? 3 : (CPT == 4 ? 2 : 1);
+            constexpr int SH = (CPT == 8) ? 3 : 2;
             constexpr int MG = VMARGIN / CPT;
             const int lane = tid & 31;
             int* r = red[d][red_i];
@@ -1161,7 +1192,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             }
             __syncwarp();
             if constexpr (VEC)
-                wf_cells_v<BITS, TWO, CPT>(reinterpret_cast<short*>(ws), ioff, dsc, dsc + 16, rg.lo, rg.hi, fast_lo, fast_hi, wlo, whi, reinterpret_cast<const uint2*>(sv.pw),
+                wf_cells_v<BITS, TWO, WS>(ws, ioff, dsc, dsc + 16, rg.lo, rg.hi, fast_lo, fast_hi, wlo, whi, reinterpret_cast<const uint2*>(sv.pw),
                                            reinterpret_cast<const uint2*>(sv.tw), sv.p0, sv.t0, sv.plen, sv.tlen, k_end, comp_end, r, gwarp, gnw, pf_off,
                                            hist ? nullptr : blk_of(d, slot));
             return rg;
@@ -1213,7 +1244,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         };
         // score-0 wavefront (wavefront_unialign_init_end2end): cell 0 of component `cb` inside a NULL-filled neighbourhood
         auto v_init_row = [&](int d, int mbase, bool hist, const SeqView& sv, int cb, int ce, int k_end, int& akM_out) -> bool {
-            constexpr int SH = (CPT == 8) ? 3 : (CPT == 4 ? 2 : 1);
+            constexpr int SH = (CPT == 8) ? 3 : 2;
             constexpr int MG = VMARGIN / CPT;
             int* r = red[d][red_i];
             SlotMeta& mt = ring_meta[mbase];
@@ -1228,23 +1259,23 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 hist_used = (long long)NCOMP * cstride;
             }
             if constexpr (VEC) {
-                short* row = reinterpret_cast<short*>(ws) + out_off + comp_idx(cb) * cstride;
+                WS* row = ws + out_off + comp_idx(cb) * cstride;
                 if (tid <= 2 * MG) {
                     const int kc = (tid - MG) << SH;
-                    uint32_t v[CPT / 2];
+                    uint32_t v[4];
 #pragma unroll
-                    for (int i = 0; i < CPT / 2; ++i) v[i] = NULL16X2;
+                    for (int i = 0; i < 4; ++i) v[i] = VecT<WS>::NULLW;
                     if (kc == 0) {
                         int m = 0;
                         if (cb == AW_COMP_M)
                             m = lcp2(reinterpret_cast<const uint2*>(sv.pw), reinterpret_cast<const uint2*>(sv.tw), sv.p0, sv.t0, min(sv.plen, sv.tlen));
-                        v[0] = (v[0] & 0xffff0000u) | ((uint32_t)m & 0xffffu);
+                        v[0] = (sizeof(WS) == 2) ? ((v[0] & 0xffff0000u) | ((uint32_t)m & 0xffffu)) : (uint32_t)m;
                         r[RED_AKM] = (cb == AW_COMP_M) ? 2 * m : INT_MIN;
                         r[RED_AKALL] = 2 * m;
                         if (cb == ce && k_end == 0) r[RED_END] = m;
                         if (!hist) *reinterpret_cast<int2*>(blk_of(d, 0)) = make_int2((cb == AW_COMP_M) ? 2 * m : INT_MIN, 2 * m);
                     }
-                    if (kc >= clo && kc + CPT - 1 <= chi) st_vec<CPT>(row + kc, v);
+                    if (kc >= clo && kc + CPT - 1 <= chi) st_vec<WS>(row + kc, v);
                 }
             }
             if (tid < 32) {
@@ -1428,7 +1459,8 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     static_assert(OV_CH <= 32 * OV_U, "a warp chunk must fit OV_U diagonals per lane");
                     const int grid0 = VEC ? m0.bk0 : kmin_alloc;
                     if (tid < 32) {
-                        int ncand = 0, nchunk = 0;
+                        int ncand = 0;
+                        int a1m = INT_MIN, a1a = INT_MIN, gmin = INT_MAX, gmax = INT_MIN;  // best antidiagonal bound of A1 per class, candidates' span
                         const int ntests = min(scope, s1 + 1) * 5;
                         for (int base = 0; base < ntests; base += 32) {
                             const int t = base + tid;
@@ -1446,48 +1478,69 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                                     if (ok) {
                                         const long long a0 = (c == AW_COMP_M) ? m0.akM : m0.akAll, a1 = (c == AW_COMP_M) ? m1.akM : m1.akAll;
                                         ok = a0 + a1 >= (long long)plen + tlen;  // necessary for off0 + off1 >= tlen
+                                        if (ok) {
+                                            if (c == AW_COMP_M) a1m = max(a1m, (int)a1);
+                                            else a1a = max(a1a, (int)a1);
+                                            gmin = min(gmin, klo);
+                                            gmax = max(gmax, khi);
+                                        }
                                     }
                                 }
                             }
                             const unsigned mask = __ballot_sync(0xffffffffu, ok);
-                            // inclusive warp scan of the candidates' chunk counts
-                            const int mych = ok ? (khi - grid0) / OV_CH - (klo - grid0) / OV_CH + 1 : 0;
-                            int inc = mych;
-#pragma unroll
-                            for (int o = 1; o < 32; o <<= 1) {
-                                const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                                if (tid >= o) inc += v;
-                            }
                             if (ok) {
                                 const int pos = ncand + __popc(mask & ((1u << tid) - 1u));
                                 cand[pos] = t;
                                 hitk[pos] = INT_MAX;
                                 cklo[pos] = klo;
                                 ckhi[pos] = khi;
-                                cpre[pos] = nchunk + inc - mych;
                             }
                             ncand += __popc(mask);
-                            nchunk += __shfl_sync(0xffffffffu, inc, 31);
                         }
+                        a1m = __reduce_max_sync(0xffffffffu, a1m);
+                        a1a = __reduce_max_sync(0xffffffffu, a1a);
+                        gmin = __reduce_min_sync(0xffffffffu, gmin);
+                        gmax = __reduce_max_sync(0xffffffffu, gmax);
                         if (tid == 0) {
                             s_ncand = ncand;
-                            s_nchunk = nchunk;
-                            cpre[ncand] = nchunk;
+                            s_nact = 0;
+                            s_ov[0] = (a1m == INT_MIN) ? INT_MAX : plen + tlen - a1m;  // a block of A0 needs at least this much to meet an M cell
+                            s_ov[1] = (a1a == INT_MIN) ? INT_MAX : plen + tlen - a1a;
+                            s_ov[2] = gmin;
+                            s_ov[3] = gmax;
                         }
                     }
                     cta_sync<NT>();
                     const int ncand = s_ncand;
-                    // first hit of every candidate: the scan ranges are cut into warp chunks of OV_CH diagonals and all
-                    // (candidate, chunk) pairs are spread over the warps, so the load latency is paid once, not once per candidate
+                    // blocks of A0's wavefront whose own maxima can reach any candidate at all: almost none, the wavefronts
+                    // only touch near the optimal path.  The scan then visits (candidate, active block) pairs only.
+                    const int b_lo = ncand ? (s_ov[2] - grid0) / OV_CH : 0, b_hi = ncand ? (s_ov[3] - grid0) / OV_CH : -1;
+                    bool implicit = !VEC;  // implicit list = every block between b_lo and b_hi
+                    if constexpr (VEC) {
+                        const int thr_m = s_ov[0], thr_a = s_ov[1];
+                        const int2* bl0 = reinterpret_cast<const int2*>(blk_of(d0, slot0));
+                        for (int b = b_lo + tid; b <= b_hi; b += NT) {
+                            const int2 v = bl0[b];
+                            if (v.x >= thr_m || v.y >= thr_a) {
+                                const int pos = atomicAdd(&s_nact, 1);
+                                if (pos < ACT_MAX) s_act[pos] = b;
+                            }
+                        }
+                        cta_sync<NT>();
+                        implicit = s_nact > ACT_MAX;
+                    }
+                    const int nact = implicit ? (b_hi - b_lo + 1) : s_nact;
                     {
-                        const int nchunk = s_nchunk, lane = tid & 31;
-                        int j = 0;
-                        for (int fc = tid >> 5; fc < nchunk; fc += NT / 32) {
-                            while (cpre[j + 1] <= fc) ++j;
-                            const int b0 = (cklo[j] - grid0) / OV_CH + (fc - cpre[j]);
-                            const int max_lo = max(cklo[j], grid0 + b0 * OV_CH), min_hi = min(ckhi[j], grid0 + b0 * OV_CH + OV_CH - 1);
+                        const int lane = tid & 31;
+                        const long long nitems = (long long)ncand * nact;
+                        for (long long item = tid >> 5; item < nitems; item += NT / 32) {
+                            const int j = (int)(item / nact), a = (int)(item - (long long)j * nact);
+                            const int b0 = implicit ? b_lo + a : s_act[a];
+                            const int kb = grid0 + b0 * OV_CH;
+                            const int max_lo = max(cklo[j], kb), min_hi = min(ckhi[j], kb + OV_CH - 1);
+                            if (max_lo > min_hi) continue;
                             const int kbase = max_lo;
-                            if (hitk[j] < kbase) continue;  // an earlier chunk already holds a hit
+                            if (hitk[j] < kbase) continue;  // an earlier block already holds a hit
                             const int t = cand[j], i = t / 5, c = test_comp(t - 5 * i);
                             const int sl1 = slot_back(cur_slot[d1], i);
                             const SlotMeta& m1 = ring_meta[d1 * ring_n + sl1];
