@@ -175,3 +175,92 @@ def test_wfa_orientation(oracle, gpu_ctx):
     for r, (q, t) in zip(res, pairs):
         o = oracle.align_pair(seqs[q], seqs[t], q, t, p, use_mash=False, qname=ids[q], tname=ids[t])
         assert r["is_reverse"] == bool(o["is_reverse"]) == (rc[q] != rc[t]) and r["paf"] == o["paf"] and r["score"] == o["score"]
+
+
+def test_c4_shape_long_pairs(oracle, gpu_ctx):
+    """BASELINE config 4 shape at reduced length: haplotypes with SVs, too long for int16 offsets -> the int32 chunked
+    path with sequences staged in global memory, biWFA recursion over many levels"""
+    c, ids, seqs, _ = synth.config("C4", n=3, length=24000)
+    assert max(len(s) for s in seqs) * 3 > 32000
+    _compare(oracle, gpu_ctx, ids, seqs, [(0, 1), (1, 2), (2, 0)], DEFAULT)
+
+
+@pytest.mark.parametrize("pen", [DEFAULT, AFFINE], ids=["affine2p", "affine"])
+def test_int16_boundary_lengths(oracle, gpu_ctx, pen):
+    """pairs just below / above the int16 storage limit (2*tlen+plen < 32000) take different kernels"""
+    ids, seqs, _ = synth.generate(4242, 2, 10800, 0.02)
+    a, b = seqs
+    cases = [(a[:10600], b[:10600]), (a[:10700], b[:10700]), (a[:10660], b[:10500]), (a[:9000], b[:10800])]
+    for x, y in cases:
+        _compare(oracle, gpu_ctx, ["x", "y"], [x, y], [(0, 1), (1, 0)], pen)
+
+
+def test_kernel_variants_agree(gpu_ctx):
+    """the same pairs through every storage / CTA-size variant of the alignment kernel give identical PAF"""
+    c, ids, seqs, _ = synth.config("C2", n=6, length=6000)
+    pairs = _all_pairs(6)
+    p = aw.make_params(**DEFAULT)
+    ctx = aw.Context(0)
+    try:
+        ctx.load_sequences(ids, seqs)
+        base = [r["paf"] for r in ctx.align_pairs(p, pairs, orientation=aw.AW_ORIENT_MASH)]
+        for opts in (dict(threads_per_cta=256), dict(threads_per_cta=256, ws16=0), dict(threads_per_cta=128, ctas_per_sm=1), dict(threads_per_cta=32)):
+            c2 = aw.Context(0)
+            for k, v in opts.items():
+                c2.set_option(k, v)
+            c2.load_sequences(ids, seqs)
+            got = [r["paf"] for r in c2.align_pairs(p, pairs, orientation=aw.AW_ORIENT_MASH)]
+            c2.close()
+            assert got == base, opts
+    finally:
+        ctx.close()
+
+
+def _check_cigar(q, t, cg, pen):
+    """applies a cg:Z: string (= match, X mismatch, I consumes query, D consumes target) and returns the penalty"""
+    import re
+
+    i = j = 0
+    penalty = 0
+    for n, op in re.findall(r"(\d+)([=XID])", cg):
+        n = int(n)
+        if op == "=":
+            assert q[i:i + n] == t[j:j + n]
+            i += n
+            j += n
+        elif op == "X":
+            assert all(q[i + k] != t[j + k] for k in range(n))
+            penalty += n * pen["mismatch"]
+            i += n
+            j += n
+        else:
+            g = pen["gap_open"] + n * pen["gap_extend"]
+            if pen.get("gap2_open") is not None:
+                g = min(g, pen["gap2_open"] + n * pen["gap2_extend"])
+            penalty += g
+            if op == "I":
+                i += n
+            else:
+                j += n
+    assert (i, j) == (len(q), len(t))
+    return penalty
+
+
+def test_c2_full_size_properties(gpu_ctx):
+    """BASELINE config 2 at full sequence size, 600 pairs: every CIGAR is a valid global alignment of its two
+    sequences whose penalty equals -score, forward/backward pairs score the same, and the PAF columns agree"""
+    c, ids, seqs, _ = synth.config("C2", n=40)
+    pairs = [(i, (i + s) % 40) for s in range(1, 16) for i in range(40)]
+    gpu_ctx.load_sequences(ids, seqs)
+    res = gpu_ctx.align_pairs(aw.make_params(**DEFAULT), pairs, orientation=aw.AW_ORIENT_MASH)
+    score = {}
+    for r, (q, t) in zip(res, pairs):
+        assert r["status"] == 0 and not r["is_reverse"]
+        assert _check_cigar(seqs[q], seqs[t], r["cg"], DEFAULT) == -r["score"]
+        f = r["paf"].split("\t")
+        assert (f[0], int(f[1]), int(f[3]), f[5], int(f[6]), int(f[8])) == (ids[q], len(seqs[q]), len(seqs[q]), ids[t], len(seqs[t]), len(seqs[t]))
+        assert int(f[10]) == max(len(seqs[q]), len(seqs[t])) and int(f[9]) == r["num_matches"]
+        score[(q, t)] = r["score"]
+    for (q, t), s in score.items():
+        if (t, q) in score:
+            assert score[(t, q)] == s
