@@ -28,6 +28,12 @@ namespace awk {
 #ifndef AW_L1_PREFETCH
 #define AW_L1_PREFETCH 0  // int16 path: after a step, prefetch into L1 the row chunks the next step will read (measured: -3 % on C2, off)
 #endif
+#ifndef AW_PREFETCH_NEXT_ITER
+#define AW_PREFETCH_NEXT_ITER 1  // chunked path: prefetch (L1) the rows of a warp's next iteration while it computes the current one
+#endif
+#ifndef AW_LOAD_CG
+#define AW_LOAD_CG 0  // chunked path: 1 = row loads bypass L1 (ld.global.cg)
+#endif
 #ifndef AW_REGS
 #define AW_REGS 128  // register budget per thread of the CTA-per-pair kernels: resident CTAs per SM = 65536 / (NT * AW_REGS)
 #endif
@@ -446,7 +452,12 @@ struct VecT<int> {
 
 template <class WS>
 __device__ __forceinline__ void ld_vec(const WS* __restrict__ p, uint32_t (&v)[4]) {
+#if AW_LOAD_CG
+    uint4 t;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "l"(p));
+#else
     const uint4 t = *reinterpret_cast<const uint4*>(p);
+#endif
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 template <class WS>
@@ -543,6 +554,20 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
                     ld_vec<WS>(pk + o_mo2, mo2);
                     ld_vec<WS>(pk + o_i2e, ie2);
                     ld_vec<WS>(pk + o_d2e, de2);
+                }
+                if (AW_PREFETCH_NEXT_ITER && cw + gnw * OWN <= c_hi) {
+                    // this warp's next iteration reads the same rows gnw*OWN chunks further on: request those lines now so that
+                    // only the first iteration of a step waits for L2 / HBM
+                    const WS* pn = pk + gnw * OWN * CPT;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_mx));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_mo1));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_i1e));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_d1e));
+                    if (TWO) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_mo2));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_i2e));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_d2e));
+                    }
                 }
             } else {
                 load_row<WS>(ws, o_mx, dsc[IN_MX], dsc[8 + IN_MX], kc, mx);
