@@ -20,7 +20,9 @@
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <mutex>
 #include <optional>
+#include <thread>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -363,6 +365,35 @@ inline std::vector<std::pair<size_t, size_t>> build_pair_list(Context& ctx, cons
 
 using Callback = std::function<void(const AlignmentResult&)>;  // throw to abort the run (mirrors a callback Err)
 
+// ---- multi-GPU sharding: the path shards by independent pairs, every GPU holds the whole sequence store,
+// only results are gathered, so there is no collective.  Pairs are assigned longest-processing-time-first to the
+// least-loaded GPU by predicted cost ~ wavefront cells = (max(len) * divergence + |len difference|)^2.
+inline double predicted_pair_cost(uint64_t len_q, uint64_t len_t, double divergence = 0.05) {
+    const double s = (double)std::max(len_q, len_t) * std::max(divergence, 1e-4) + (double)(len_q > len_t ? len_q - len_t : len_t - len_q);
+    return s * s + (double)(len_q + len_t);
+}
+// returns n_parts lists of indices into `pairs`, each ascending; deterministic
+inline std::vector<std::vector<size_t>> partition_pairs(const std::vector<std::pair<size_t, size_t>>& pairs, const std::vector<Sequence>& seqs,
+                                                        size_t n_parts) {
+    std::vector<std::vector<size_t>> shards(std::max<size_t>(1, n_parts));
+    if (n_parts <= 1) {
+        shards[0].resize(pairs.size());
+        for (size_t i = 0; i < pairs.size(); ++i) shards[0][i] = i;
+        return shards;
+    }
+    std::vector<std::pair<double, size_t>> costed(pairs.size());
+    for (size_t i = 0; i < pairs.size(); ++i) costed[i] = {predicted_pair_cost(seqs[pairs[i].first].seq.size(), seqs[pairs[i].second].seq.size()), i};
+    std::sort(costed.begin(), costed.end(), [](const auto& a, const auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
+    std::vector<double> load(n_parts, 0.0);
+    for (const auto& c : costed) {
+        const size_t r = (size_t)(std::min_element(load.begin(), load.end()) - load.begin());
+        shards[r].push_back(c.second);
+        load[r] += c.first;
+    }
+    for (auto& s : shards) std::sort(s.begin(), s.end());
+    return shards;
+}
+
 class AllPairIterator {
    public:
     // AllPairIterator::new (src/iterator.rs:25-28) == with_options(seqs, params, true, false, None)
@@ -384,6 +415,36 @@ class AllPairIterator {
     void for_each_with_callback(const Callback& cb, uint32_t flags = 0) {
         run(next_, pairs_.size() - next_, cb, flags);
         next_ = pairs_.size();
+    }
+    // the same over several GPUs: `others` are further contexts that hold the same sequences; one host thread per GPU
+    // aligns its shard of the remaining pair list, the callback is serialised (completion order, like the reference's
+    // rayon workers), the first callback / device error cancels that GPU's shard and is rethrown after the join
+    void for_each_with_callback_multi(const std::vector<Context*>& others, const Callback& cb, uint32_t flags = 0) {
+        std::vector<Context*> ctxs{&ctx_};
+        ctxs.insert(ctxs.end(), others.begin(), others.end());
+        std::vector<std::pair<size_t, size_t>> rest(pairs_.begin() + next_, pairs_.end());
+        next_ = pairs_.size();
+        const auto shards = partition_pairs(rest, seqs_, ctxs.size());
+        std::mutex mu;
+        std::vector<std::exception_ptr> errs(ctxs.size());
+        const Callback locked = [&](const AlignmentResult& r) {
+            std::lock_guard<std::mutex> g(mu);
+            cb(r);
+        };
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < ctxs.size(); ++g)
+            th.emplace_back([&, g] {
+                try {
+                    std::vector<std::pair<size_t, size_t>> mine(shards[g].size());
+                    for (size_t i = 0; i < mine.size(); ++i) mine[i] = rest[shards[g][i]];
+                    run_on(*ctxs[g], mine, 0, mine.size(), locked, flags);
+                } catch (...) {
+                    errs[g] = std::current_exception();
+                }
+            });
+        for (auto& t : th) t.join();
+        for (auto& e : errs)
+            if (e) std::rethrow_exception(e);
     }
     // impl Iterator::next (src/iterator.rs:151-171): strictly in pair order; batches are prefetched
     std::optional<AlignmentResult> next() {
@@ -429,7 +490,8 @@ class AllPairIterator {
         }
         return 0;
     }
-    void run(size_t first, size_t count, const Callback& cb, uint32_t flags) {
+    void run(size_t first, size_t count, const Callback& cb, uint32_t flags) { run_on(ctx_, pairs_, first, count, cb, flags); }
+    void run_on(Context& ctx_, const std::vector<std::pair<size_t, size_t>>& pairs_, size_t first, size_t count, const Callback& cb, uint32_t flags) {
         if (count == 0) return;
         std::vector<aw_pair> cp(count);
         for (size_t i = 0; i < count; ++i) {

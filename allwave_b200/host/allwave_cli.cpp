@@ -5,13 +5,14 @@
 #include <chrono>
 #include <cstdio>
 #include <iostream>
+#include <memory>
 
 #include "allwave.hpp"
 
 int main(int argc, char** argv) {
     std::string input, output, scores = "0,5,8,2,24,1", spars = "giant:0.99";
     bool wfa_orientation = false, progress = true;
-    int device = 0;
+    int device = 0, gpus = 1;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto need = [&](const char* name) -> std::string {
@@ -27,10 +28,11 @@ int main(int argc, char** argv) {
         else if (a == "-p" || a == "--sparsification") spars = need("-p");
         else if (a == "-t" || a == "--threads") (void)need("-t");  // host threads are irrelevant: pairs run on the GPU
         else if (a == "--gpu") device = std::atoi(need("--gpu").c_str());
+        else if (a == "--gpus") gpus = std::max(1, std::atoi(need("--gpus").c_str()));  // devices device .. device+gpus-1, pairs sharded by predicted cost
         else if (a == "--wfa-orientation") wfa_orientation = true;
         else if (a == "--no-progress") progress = false;
         else {
-            std::fprintf(stderr, "usage: allwave -i FASTA [-o PAF] [-s scores] [-p none|auto|random:f|giant:p|tree:n:f:r[:k]] [--wfa-orientation] [--gpu D]\n");
+            std::fprintf(stderr, "usage: allwave -i FASTA [-o PAF] [-s scores] [-p none|auto|random:f|giant:p|tree:n:f:r[:k]] [--wfa-orientation] [--gpu D] [--gpus N]\n");
             return 2;
         }
     }
@@ -45,16 +47,25 @@ int main(int argc, char** argv) {
         const std::vector<Sequence> seqs = read_fasta(input);
         Context ctx(device);
         ctx.load(seqs);
+        std::vector<std::unique_ptr<Context>> more;
+        std::vector<Context*> others;
+        for (int g = 1; g < gpus; ++g) {
+            more.emplace_back(new Context(device + g));
+            more.back()->load(seqs);
+            others.push_back(more.back().get());
+        }
         AllPairIterator it(ctx, seqs, params, true, !wfa_orientation, sp);
         FILE* out = output.empty() ? stdout : std::fopen(output.c_str(), "w");
         if (!out) throw std::runtime_error("cannot open " + output);
         const auto t0 = std::chrono::steady_clock::now();
         size_t done = 0;
-        it.for_each_with_callback([&](const AlignmentResult& r) {
+        const Callback write_line = [&](const AlignmentResult& r) {
             std::fwrite(r.paf.data(), 1, r.paf.size(), out);
             std::fputc('\n', out);
             ++done;
-        });
+        };
+        if (others.empty()) it.for_each_with_callback(write_line);
+        else it.for_each_with_callback_multi(others, write_line);
         if (out != stdout) std::fclose(out);
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (progress) std::fprintf(stderr, "[%.1fs] %zu/%zu (100.0%%) %.1f alignments/sec - Complete!\n", dt, done, it.pair_count(), done / std::max(dt, 1e-9));

@@ -264,3 +264,22 @@ def test_c2_full_size_properties(gpu_ctx):
     for (q, t), s in score.items():
         if (t, q) in score:
             assert score[(t, q)] == s
+
+
+def test_cli_multi_gpu_matches_single(tmp_path):
+    """allwave --gpus N (pairs sharded by predicted cost, one host thread per GPU, no collective) writes the same set of
+    PAF lines as one GPU; needs >= 2 devices"""
+    import subprocess
+
+    if aw._cabi.lib().aw_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    c, ids, seqs, _ = synth.config("C5", n=24, length=3000)
+    fa = tmp_path / "in.fa"
+    fa.write_text("".join(f">{i}\n{s.decode()}\n" for i, s in zip(ids, seqs)))
+    exe = os.path.join(os.path.dirname(aw._cabi.so_path()), "allwave")
+    outs = []
+    for g in (1, 2):
+        out = tmp_path / f"out{g}.paf"
+        subprocess.check_call([exe, "-i", str(fa), "-o", str(out), "-p", "none", "--no-progress", "--gpus", str(g)])
+        outs.append(sorted(out.read_text().splitlines()))
+    assert len(outs[0]) == 24 * 23 and outs[0] == outs[1]
