@@ -34,6 +34,9 @@ namespace awk {
 #ifndef AW_LOAD_CG
 #define AW_LOAD_CG 0  // chunked path: 1 = row loads bypass L1 (ld.global.cg)
 #endif
+#ifndef AW_CYCLE_COUNTERS
+#define AW_CYCLE_COUNTERS 0  // (build with -DAW_CYCLE_COUNTERS=1 for tools/perf_probe.py) per-phase device-clock breakdown in AwPairOut::cyc (aw_batch_debug_cycles); 0 frees ~14 registers
+#endif
 #ifndef AW_REGS
 #define AW_REGS 128  // register budget per thread of the CTA-per-pair kernels: resident CTAs per SM = 65536 / (NT * AW_REGS)
 #endif
@@ -989,11 +992,13 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
 
         int status = seq_fits ? ST_OK : ST_FAIL_WORKSPACE;
         unsigned long long cyc[6] = {0, 0, 0, 0, 0, 0};
-        long long tmark = clock64();
+        long long tmark = AW_CYCLE_COUNTERS ? clock64() : 0;
         auto lap = [&](int i) {
-            const long long t = clock64();
-            cyc[i] += (unsigned long long)(t - tmark);
-            tmark = t;
+            if (AW_CYCLE_COUNTERS) {
+                const long long t = clock64();
+                cyc[i] += (unsigned long long)(t - tmark);
+                tmark = t;
+            }
         };
         unsigned long long w_cells = 0;
         unsigned w_steps = 0, w_bps = 0, w_base = 0, w_maxbase = 0;
