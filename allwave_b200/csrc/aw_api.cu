@@ -15,9 +15,6 @@
 #include "aw_common.cuh"
 #include "aw_sketch.cuh"
 #include "aw_wfa.cuh"
-#ifndef AW_ENABLE_BAND
-#define AW_ENABLE_BAND 0
-#endif
 
 static thread_local char g_err[512] = "";
 void aw_set_error(const char* fmt, ...) {
@@ -175,7 +172,6 @@ struct aw_ctx {
     int64_t max_w = 1 << 20;   // cap on allocated diagonals per wavefront (first attempt)
     int64_t hist_mb = 16;      // base-case history arena per CTA (first attempt)
     int64_t chunk_pairs = 65536;
-    int band_engine = 0;       // 1 = use the shared-memory diagonal-band engine for phase 1 (experimental)
     int ws16 = 1;              // 1 = int16 wavefront storage when every offset fits
     aw_params orient_params = {0, 1, 1, 1, 0, 0, 0, 0};  // AlignmentParams::edit_distance(), src/iterator.rs:85
     // sequence store
@@ -321,7 +317,7 @@ extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
     } else if (k == "max_wavefront_width") c->max_w = value;
     else if (k == "hist_mb") c->hist_mb = value;
     else if (k == "chunk_pairs") c->chunk_pairs = value > 0 ? value : 65536;
-    else if (k == "band_engine") c->band_engine = value ? 1 : 0;
+    else if (k == "band_engine") (void)value;  // accepted for compatibility: the experimental band engine of the first kernels is gone
     else if (k == "ws16") c->ws16 = value ? 1 : 0;
     else return AW_EINVAL;
     return AW_OK;
@@ -716,7 +712,7 @@ cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStrea
 
 cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bool ws16, int grid, cudaStream_t st) {
     const int scope = P.pen.scope;
-    size_t smem = sizeof(awk::SlotMeta) * 2 * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt + sizeof(int) * (15 * scope + 4);
+    size_t smem = sizeof(awk::SlotMeta) * 2 * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt + sizeof(int) * (10 * scope + 4);
 #define AW_CASE(NT_, BITS_, TWO_, WS_, W16_) \
     if (nt == NT_ && bits == BITS_ && two == TWO_ && ws16 == W16_) return launch_align<NT_, BITS_, TWO_, WS_>(P, grid, smem, st);
 #ifndef AW_FAST_BUILD  // dev builds (-DAW_FAST_BUILD) keep only the two-piece 2-bit int16 kernels

@@ -876,7 +876,6 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     unsigned long long* scanbuf = reinterpret_cast<unsigned long long*>(hitk + scope * 5);  // [NT]; 8-byte aligned: sizeof(SlotMeta)*2*ring_n + 40*scope
     int* cklo = reinterpret_cast<int*>(scanbuf + NT);                                      // [scope*5] first diagonal of a candidate's scan range
     int* ckhi = cklo + scope * 5;                                                          // [scope*5] last diagonal
-    int* cpre = ckhi + scope * 5;                                                          // [scope*5+1] first warp chunk of a candidate
     __shared__ int red[2][3][NRED];
     __shared__ SubProblem stack[MAX_STACK];
     __shared__ unsigned s_next;

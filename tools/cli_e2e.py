@@ -23,7 +23,7 @@ p = O.params(sc[0], sc[1], sc[2], sc[3], sc[4] if len(sc) > 4 else None, sc[5] i
 idx = {name: i for i, name in enumerate(ids)}
 rnd = random.Random(1)
 bad = 0
-sample = rnd.sample(lines, min(24, len(lines)))
+sample = rnd.sample(lines, min(int(os.environ.get("AW_CHECK", "24")), len(lines)))
 for ln in sample:
     f = ln.split("\t")
     q, t = idx[f[0]], idx[f[5]]
