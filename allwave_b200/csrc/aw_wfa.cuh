@@ -634,25 +634,30 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
                     if (j == q) val = T::get(src, q);
                 red[RED_END] = val;
             }
+            // Per-cell scalar part, written with masks instead of conditionals: ptxas turns `valid ? .. : ..` blocks into
+            // one branch region per cell (BSSY/BSYNC), which serialises the CPT independent chains; pure ALU code lets it
+            // interleave them.
             int mm[CPT];
             unsigned more = 0;
+            int oobm = 0;
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int k = kc + j;
                 const int m = T::get(vM, j);
                 const int v = m - k;
                 const int maxlen = min(s_plen - v, s_tlen - m);
-                const bool valid = (m | v | maxlen) >= 0;  // 0 <= h <= tlen and 0 <= v <= plen
-                if (m >= 0) {
-                    akAll_b = max(akAll_b, m + v);  // 2*off - k; m (pre-null) dominates every component at k
-                    oob = oob || !valid;
-                }
-                // first round of the extension (16 symbols), branch-free; invalid cells compare position 0
-                const uint32_t x = load16(s_p2, s_p0 + (valid ? v : 0)) ^ load16(s_t2, s_t0 + (valid ? m : 0));
-                const int cnt = __clz(__brev(x)) >> 1;  // 16 when the whole word matches
-                mm[j] = valid ? m + min(cnt, maxlen) : -1;
-                if (valid && x == 0 && maxlen > 16) more |= 1u << j;
+                const int vmask = ~((m | v | maxlen) >> 31);  // all ones iff 0 <= h <= tlen and 0 <= v <= plen
+                const int nonneg = ~(m >> 31);
+                akAll_b = max(akAll_b, ((m + v) & nonneg) | (INT_MIN & ~nonneg));  // 2*off - k; m (pre-null) dominates every component at k
+                oobm |= nonneg & ~vmask;                                           // a non-null offset outside the sequences
+                // first round of the extension (16 symbols); invalid cells compare position 0
+                const uint32_t x = load16(s_p2, s_p0 + (v & vmask)) ^ load16(s_t2, s_t0 + (m & vmask));
+                const int cnt = __popc((x - 1u) & ~x) >> 1;  // matching symbols = trailing zero pairs; 16 when the whole word matches
+                const int ext = min(cnt, maxlen);
+                mm[j] = ((m + ext) & vmask) | (T::NULLV & ~vmask);
+                more |= (unsigned)((cnt >> 4) & ((16 - maxlen) >> 31) & vmask & 1) << j;  // whole word matched and symbols remain
             }
+            oob = oob || (oobm != 0);
             while (more) {  // long match runs: continue word by word, one cell at a time (kept small: instruction-cache footprint)
                 const int j = __ffs(more) - 1;
                 more &= more - 1;
@@ -668,9 +673,16 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
             }
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                if (mm[j] >= 0) akM_b = max(akM_b, 2 * mm[j] - (kc + j));
-                else mm[j] = T::NULLV;
-                if (comp_end == AW_COMP_M && kc + j == k_end) red[RED_END] = mm[j];
+                const int nonneg = ~(mm[j] >> 31);
+                akM_b = max(akM_b, ((2 * mm[j] - (kc + j)) & nonneg) | (INT_MIN & ~nonneg));
+            }
+            if (comp_end == AW_COMP_M && k_end >= kc && k_end < kc + CPT) {
+                const int j = k_end - kc;
+                int val = mm[0];
+#pragma unroll
+                for (int q = 1; q < CPT; ++q)
+                    if (j == q) val = mm[q];
+                red[RED_END] = val;
             }
 #pragma unroll
             for (int i = 0; i < VW; ++i) {
