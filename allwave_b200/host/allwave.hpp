@@ -416,6 +416,21 @@ class AllPairIterator {
         run(next_, pairs_.size() - next_, cb, flags);
         next_ = pairs_.size();
     }
+    // PAF-only fast path of the CLI writer (src/main.rs:347-374): hands out the GPU-formatted line without building an
+    // AlignmentResult (three heap strings per pair dominate the host time on short-read workloads)
+    using PafCallback = std::function<void(const char*, size_t)>;
+    void for_each_paf(const PafCallback& cb, const std::vector<Context*>& others = {}) {
+        const Callback adapt = [&](const AlignmentResult& r) { cb(r.paf.data(), r.paf.size()); };
+        paf_only_ = &cb;
+        try {
+            if (others.empty()) for_each_with_callback(adapt);
+            else for_each_with_callback_multi(others, adapt);
+        } catch (...) {
+            paf_only_ = nullptr;
+            throw;
+        }
+        paf_only_ = nullptr;
+    }
     // the same over several GPUs: `others` are further contexts that hold the same sequences; one host thread per GPU
     // aligns its shard of the remaining pair list, the callback is serialised (completion order, like the reference's
     // rayon workers), the first callback / device error cancels that GPU's shard and is rethrown after the join
@@ -431,6 +446,7 @@ class AllPairIterator {
             std::lock_guard<std::mutex> g(mu);
             cb(r);
         };
+        paf_mu_ = &mu;
         std::vector<std::thread> th;
         for (size_t g = 0; g < ctxs.size(); ++g)
             th.emplace_back([&, g] {
@@ -443,6 +459,7 @@ class AllPairIterator {
                 }
             });
         for (auto& t : th) t.join();
+        paf_mu_ = nullptr;
         for (auto& e : errs)
             if (e) std::rethrow_exception(e);
     }
@@ -465,9 +482,25 @@ class AllPairIterator {
         const Callback* cb;
         std::exception_ptr err;
         uint32_t flags;
+        const PafCallback* paf_only;
+        std::mutex* mu;
     };
     static int c_callback(const aw_result* r, void* user) {
         Trampoline* t = static_cast<Trampoline*>(user);
+        if (t->paf_only) {
+            try {
+                if (t->mu) {
+                    std::lock_guard<std::mutex> g(*t->mu);
+                    (*t->paf_only)(r->paf, r->paf_len);
+                } else {
+                    (*t->paf_only)(r->paf, r->paf_len);
+                }
+            } catch (...) {
+                t->err = std::current_exception();
+                return 1;
+            }
+            return 0;
+        }
         AlignmentResult a;
         a.query_idx = r->query_idx;
         a.target_idx = r->target_idx;
@@ -504,7 +537,7 @@ class AllPairIterator {
             int rco = aw_set_orientation_params(ctx_.get(), &op);
             if (rco != AW_OK) throw std::runtime_error(std::string("aw_set_orientation_params: ") + aw_strerror(rco) + ": " + aw_last_error());
         }
-        Trampoline t{&cb, nullptr, flags};
+        Trampoline t{&cb, nullptr, flags, paf_only_, paf_mu_};
         int rc = aw_align_pairs(ctx_.get(), &p, use_mash_ ? AW_ORIENT_MASH : AW_ORIENT_WFA, cp.data(), count, flags, &c_callback, &t);
         if (t.err) std::rethrow_exception(t.err);
         if (rc != AW_OK) throw std::runtime_error(std::string("aw_align_pairs: ") + aw_strerror(rc) + ": " + aw_last_error());
@@ -514,6 +547,8 @@ class AllPairIterator {
     AlignmentParams params_, orientation_params_;
     bool exclude_self_, use_mash_;
     std::vector<std::pair<size_t, size_t>> pairs_;
+    const PafCallback* paf_only_ = nullptr;
+    std::mutex* paf_mu_ = nullptr;
     size_t next_ = 0, prefetch_ = 4096, buf_pos_ = 0;
     std::vector<AlignmentResult> buffered_;
 };

@@ -59,13 +59,13 @@ int main(int argc, char** argv) {
         if (!out) throw std::runtime_error("cannot open " + output);
         const auto t0 = std::chrono::steady_clock::now();
         size_t done = 0;
-        const Callback write_line = [&](const AlignmentResult& r) {
-            std::fwrite(r.paf.data(), 1, r.paf.size(), out);
-            std::fputc('\n', out);
-            ++done;
-        };
-        if (others.empty()) it.for_each_with_callback(write_line);
-        else it.for_each_with_callback_multi(others, write_line);
+        it.for_each_paf(
+            [&](const char* line, size_t len) {
+                std::fwrite(line, 1, len, out);
+                std::fputc('\n', out);
+                ++done;
+            },
+            others);
         if (out != stdout) std::fclose(out);
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (progress) std::fprintf(stderr, "[%.1fs] %zu/%zu (100.0%%) %.1f alignments/sec - Complete!\n", dt, done, it.pair_count(), done / std::max(dt, 1e-9));
