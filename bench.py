@@ -176,7 +176,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
-    B = args.batch or 2368  # 4 pairs per resident CTA (148 SMs x 4 CTAs)
+    B = args.batch or 9472  # 16 pairs per resident CTA (148 SMs x 4 CTAs): long enough that the last wave's tail is small
     ids, seqs = c2_sequences(args.nseq)
     # whole job = world*B pairs; host-side greedy (LPT) partition by predicted cost, no collective
     job = job_pairs(args.nseq, B * world)
