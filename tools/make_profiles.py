@@ -34,7 +34,7 @@ summary = {
     "launch_shares": {k: {"share": v / s, "launches": cnt[k], "total_ms": v / 1e6} for k, v in tot.most_common()},
     "align_kernel": {
         "name": m.get("Kernel Name", "aw_align_kernel"), "grid": m.get("launch__grid_size"), "block": m.get("launch__block_size"), "regs": m.get("launch__registers_per_thread"),
-        "duration_ms": float(m["gpu__time_duration.sum"]) if u["gpu__time_duration.sum"] == "ms" else float(m["gpu__time_duration.sum"]) / 1e6,
+        "duration_ms": float(m["gpu__time_duration.sum"]) * {"s": 1e3, "ms": 1.0, "us": 1e-3, "ns": 1e-6}.get(u["gpu__time_duration.sum"], 1e-6),
         "dram_bytes_read": gb("dram__bytes_read.sum"), "dram_bytes_write": gb("dram__bytes_write.sum"),
         "dram_bytes_per_launch": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
         "dram_throughput_pct": float(m["gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"]),
