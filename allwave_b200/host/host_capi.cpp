@@ -98,5 +98,22 @@ uint64_t* awh_build_knn_graph(const double* m, uint64_t n, uint64_t k, int farth
     return o;
 }
 
+// partition_pairs (multi-GPU sharding): out_part[i] = GPU of pair i
+int awh_partition_pairs(const uint64_t* pairs, uint64_t npairs, const uint64_t* lens, uint64_t nseq, uint64_t nparts, uint32_t* out_part) {
+    try {
+        std::vector<Sequence> seqs(nseq);
+        for (uint64_t i = 0; i < nseq; ++i) seqs[i].seq.resize(lens[i]);
+        std::vector<std::pair<size_t, size_t>> p(npairs);
+        for (uint64_t i = 0; i < npairs; ++i) p[i] = {(size_t)pairs[2 * i], (size_t)pairs[2 * i + 1]};
+        const auto shards = partition_pairs(p, seqs, (size_t)nparts);
+        for (size_t g = 0; g < shards.size(); ++g)
+            for (size_t i : shards[g]) out_part[i] = (uint32_t)g;
+        return 0;
+    } catch (const std::exception& e) {
+        g_msg = e.what();
+        return -1;
+    }
+}
+
 void awh_free(void* p) { std::free(p); }
 }

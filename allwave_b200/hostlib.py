@@ -33,6 +33,7 @@ def lib():
         L.awh_build_knn_graph.argtypes = [C.POINTER(C.c_double), C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
         L.awh_build_knn_graph.restype = C.POINTER(C.c_uint64)
         L.awh_free.argtypes = [C.c_void_p]
+        L.awh_partition_pairs.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
 
@@ -74,3 +75,17 @@ def build_knn_graph(matrix, k, farthest):
     out = [(p[2 * i], p[2 * i + 1]) for i in range(cnt.value)]
     lib().awh_free(p)
     return out
+
+
+def partition_pairs(pairs, lens, n_parts):
+    """allwave.hpp partition_pairs (the C++ multi-GPU sharding): list of n_parts pair lists, like partition.partition_pairs"""
+    n = len(pairs)
+    pa = (C.c_uint64 * max(1, 2 * n))(*[v for p in pairs for v in p])
+    la = (C.c_uint64 * max(1, len(lens)))(*lens)
+    out = (C.c_uint32 * max(1, n))()
+    if lib().awh_partition_pairs(pa, n, la, len(lens), n_parts, out) != 0:
+        raise RuntimeError(lib().awh_last_message().decode())
+    shards = [[] for _ in range(max(1, n_parts))]
+    for i, p in enumerate(pairs):
+        shards[out[i]].append(tuple(p))
+    return shards

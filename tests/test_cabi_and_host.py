@@ -158,3 +158,23 @@ def test_host_parsers():
                      ("tree:1:1:1.5", "Random fraction must be between 0 and 1"), ("bogus", "Invalid sparsification strategy")):
         with pytest.raises(ValueError, match=msg):
             H.parse_sparsification(bad)
+
+
+def test_cpp_partition_matches_python():
+    """the C++ host's multi-GPU sharding (allwave.hpp partition_pairs) is the same LPT assignment as partition.py"""
+    import random
+
+    from allwave_b200 import hostlib as H
+    from allwave_b200 import partition
+
+    rnd = random.Random(11)
+    lens = [rnd.choice([150, 5000, 10000, 10000, 250000]) + rnd.randrange(50) for _ in range(40)]
+    pairs = [(i, j) for i in range(40) for j in range(40) if i != j and rnd.random() < 0.3]
+    for parts in (1, 2, 3, 8):
+        got = H.partition_pairs(pairs, lens, parts)
+        exp = partition.partition_pairs(pairs, lens, parts)
+        assert got == exp
+        assert sorted(p for s in got for p in s) == sorted(pairs)
+        if parts > 1:
+            loads = partition.shard_loads(got, lens)
+            assert max(loads) <= 1.25 * (sum(loads) / parts) + max(partition.predicted_cost(lens[q], lens[t]) for q, t in pairs)
