@@ -378,8 +378,9 @@ __device__ __forceinline__ void wf_cells(WS* __restrict__ ws, const In (&in)[7],
 // copies too), so there is only a forward code path.
 constexpr int SEQ2_ENTRIES = 2720;  // uint2 entries for 2 x (pattern + text): plen + tlen <= 21696 symbols
 __device__ __forceinline__ uint32_t load16(const uint2* __restrict__ s2, int pos) {
-    const uint2 e = s2[(unsigned)pos >> 4];
-    return __funnelshift_r(e.x, e.y, (pos & 15) * 2);
+    // entry pos/16 at byte offset (pos >> 1) & ~7; the funnel shift uses the low 5 bits of its amount = 2 * (pos % 16)
+    const uint2 e = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(s2) + (((unsigned)pos >> 1) & ~7u));
+    return __funnelshift_r(e.x, e.y, pos << 1);
 }
 // matching symbols from (pp, tp), at most maxlen
 __device__ __forceinline__ int lcp2(const uint2* __restrict__ p2, const uint2* __restrict__ t2, int pp, int tp, int maxlen) {
