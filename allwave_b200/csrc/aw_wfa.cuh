@@ -1,13 +1,19 @@
 // aw_wfa.cuh -- the alignment hot path as one persistent sm_100a kernel per pair class:
 //   K4 wavefront compute (gap-affine / gap-affine-2p M,I1,D1,I2,D2 recurrences)
-//   K5 match extend (XOR + ffs/clz longest common prefix on 2-bit packed or byte words)
+//   K5 match extend (XOR + popc/clz longest common prefix on 2-bit packed or byte words)
 //   K6 biWFA breakpoint search (forward/reverse wavefronts, overlap test, DFS recursion stack)
 //   K7 base case: full-history unidirectional WFA + WFA2-ordered backtrace
 //   K8 CIGAR run-length encoding, op statistics, score, PAF text
-// One CTA (NT threads; NT=32 is the one-warp-per-pair variant) owns one pair at a time and
-// pulls pairs from a global work counter.  Replaces lib_wfa2's AffineWavefronts::align as
-// driven by /root/reference/src/alignment.rs:201-261 and the CIGAR/PAF passes of
+// One CTA owns one pair at a time and pulls pairs from a global work counter.  Replaces lib_wfa2's
+// AffineWavefronts::align as driven by /root/reference/src/alignment.rs:201-261 and the CIGAR/PAF passes of
 // src/alignment.rs:292-376 + src/lib.rs:71-112.  Tie-break constants: include/aw_wfa2_compat.h.
+//
+// Two wavefront-step engines share the driver (aw_align_kernel):
+//   * chunked (VEC: 2-bit sequences, NT >= 64; int16 or int32 rows): v_launch / wf_cells_v / v_finish -- every thread owns
+//     16 bytes of consecutive diagonals, packed int16x2 recurrences, arithmetic trim, block maxima for the overlap test;
+//   * scalar (byte sequences or the one-warp NT=32 kernels): launch_dir / wf_cells / finish_dir -- one diagonal per thread
+//     per iteration with explicit edge tracking.
+// DESIGN.md section 4 describes both and lists the measured experiments behind the compile-time flags below.
 #pragma once
 #include <limits.h>
 
@@ -17,7 +23,7 @@ namespace awk {
 
 #define AW_KFLAG_COUNT_ONLY 0x100u  // internal: statistics only (orientation passes), no text output
 #ifndef AW_PREFETCH_STEPS
-#define AW_PREFETCH_STEPS 0  // int16 path: L2 prefetch distance (score steps) for the old M rows; 0 = off (measured: no gain on C2)
+#define AW_PREFETCH_STEPS 0  // chunked path: L2 prefetch distance (score steps) for the old M rows; 0 = off (measured: no gain on C2)
 #endif
 #ifndef AW_COMPACT_ID_RINGS
 // int16 path: 1 = far from the overlap phase, I/D rows rotate through small rings (extension distance + 1 rows) so that they
@@ -26,7 +32,7 @@ namespace awk {
 #define AW_COMPACT_ID_RINGS 0
 #endif
 #ifndef AW_L1_PREFETCH
-#define AW_L1_PREFETCH 0  // int16 path: after a step, prefetch into L1 the row chunks the next step will read (measured: -3 % on C2, off)
+#define AW_L1_PREFETCH 0  // chunked path: after a step, prefetch into L1 the row chunks the next step will read (measured: -3 % on C2, off)
 #endif
 #ifndef AW_PREFETCH_NEXT_ITER
 #define AW_PREFETCH_NEXT_ITER 1  // chunked path: prefetch (L1) the rows of a warp's next iteration while it computes the current one
@@ -55,7 +61,7 @@ enum { IN_MX = 0, IN_MO1, IN_I1E, IN_D1E, IN_MO2, IN_I2E, IN_D2E };
 enum { ST_OK = 0, ST_END_REACHED = 1, ST_FAIL_WORKSPACE = 2 };
 // red[] layout: per component c: RED_HI+c = max in-bounds k, RED_LO+c = max(-k); then the two
 // antidiagonal bounds and the value at the end cell
-// int16 path only: RED_OOB = the row holds a non-null out-of-bounds cell, RED_CLO/RED_CHI = computed range of the row
+// chunked path only: RED_OOB = the row holds a non-null out-of-bounds cell, RED_CLO/RED_CHI = computed range of the row
 // (published by the planning warp), RED_FAIL = the row does not fit the workspace
 enum { RED_HI = 0, RED_LO = 5, RED_AKM = 10, RED_AKALL = 11, RED_END = 12, RED_OOB = 13, RED_CLO = 14, RED_CHI = 15, RED_FAIL = 16 };
 
