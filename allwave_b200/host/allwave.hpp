@@ -15,6 +15,8 @@
 // partitions them and forwards results.
 #pragma once
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -27,6 +29,10 @@
 #include <string>
 #include <utility>
 #include <vector>
+
+#ifdef ALLWAVE_HAVE_ZLIB
+#include <zlib.h>
+#endif
 
 #include "../../include/allwave_cuda.h"
 
@@ -574,24 +580,129 @@ inline std::vector<uint8_t> reverse_complement(const std::vector<uint8_t>& seq) 
 }
 
 // plain FASTA (src/main.rs:206-234; ids up to the first whitespace).  bgzf input is out of scope
+// FASTA ingest (src/main.rs:206-234): plain files, and .gz / bgzf files through zlib (bgzf is a series of gzip members,
+// which gzread decodes transparently) when the translation unit is built with -DALLWAVE_HAVE_ZLIB -lz
+namespace detail {
+inline void fasta_line(std::vector<Sequence>& seqs, std::string& line) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    if (line.empty()) return;
+    if (line[0] == '>') {
+        size_t e = line.find_first_of(" \t", 1);
+        seqs.push_back(Sequence{line.substr(1, e == std::string::npos ? std::string::npos : e - 1), {}});
+    } else if (!seqs.empty()) {
+        seqs.back().seq.insert(seqs.back().seq.end(), line.begin(), line.end());
+    }
+}
+}  // namespace detail
 inline std::vector<Sequence> read_fasta(const std::string& path) {
-    if (path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0)
-        throw std::runtime_error("gzipped FASTA is not supported by this driver; decompress first");
-    std::ifstream in(path);
-    if (!in) throw std::runtime_error("cannot open " + path);
     std::vector<Sequence> seqs;
     std::string line;
-    while (std::getline(in, line)) {
-        if (!line.empty() && line.back() == '\r') line.pop_back();
-        if (line.empty()) continue;
-        if (line[0] == '>') {
-            size_t e = line.find_first_of(" \t", 1);
-            seqs.push_back(Sequence{line.substr(1, e == std::string::npos ? std::string::npos : e - 1), {}});
-        } else if (!seqs.empty()) {
-            seqs.back().seq.insert(seqs.back().seq.end(), line.begin(), line.end());
+    if (path.size() > 3 && path.compare(path.size() - 3, 3, ".gz") == 0) {
+#ifdef ALLWAVE_HAVE_ZLIB
+        gzFile gz = gzopen(path.c_str(), "rb");
+        if (!gz) throw std::runtime_error("cannot open " + path);
+        gzbuffer(gz, 1 << 20);
+        std::vector<char> buf(1 << 20);
+        int n;
+        while ((n = gzread(gz, buf.data(), (unsigned)buf.size())) > 0) {
+            const char* p = buf.data();
+            const char* end = p + n;
+            while (p < end) {
+                const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+                if (!nl) {
+                    line.append(p, end);
+                    break;
+                }
+                line.append(p, nl);
+                detail::fasta_line(seqs, line);
+                line.clear();
+                p = nl + 1;
+            }
         }
+        const bool bad = n < 0;
+        gzclose(gz);
+        if (bad) throw std::runtime_error("error while decompressing " + path);
+        if (!line.empty()) detail::fasta_line(seqs, line);
+        return seqs;
+#else
+        throw std::runtime_error("gzipped FASTA needs a build with zlib (-DALLWAVE_HAVE_ZLIB -lz); decompress first");
+#endif
     }
+    std::ifstream in(path);
+    if (!in) throw std::runtime_error("cannot open " + path);
+    while (std::getline(in, line)) detail::fasta_line(seqs, line);
     return seqs;
+}
+
+// parse_ani_preset (src/main.rs:83-124): -x 95% | 95 | 0.95 -> score string
+inline std::string parse_ani_preset(const std::string& preset) {
+    double ani;
+    auto parse_num = [](const std::string& s, double& out) -> bool {
+        if (s.empty()) return false;
+        char* end = nullptr;
+        out = std::strtod(s.c_str(), &end);
+        return end && *end == 0;
+    };
+    if (preset.find('.') != std::string::npos) {
+        double v;
+        if (!parse_num(preset, v) || !(v > 0.0 && v <= 1.0)) throw std::invalid_argument("Invalid ANI value: " + preset + ". Use 0.5-1.0 or 50%-100%");
+        ani = v * 100.0;
+    } else if (!preset.empty() && preset.back() == '%') {
+        double v;
+        if (!parse_num(preset.substr(0, preset.size() - 1), v) || !(v >= 50.0 && v <= 100.0))
+            throw std::invalid_argument("Invalid ANI percentage: " + preset + ". Use 50%-100%");
+        ani = v;
+    } else {
+        double v;
+        if (!parse_num(preset, v) || !(v >= 50.0 && v <= 100.0)) throw std::invalid_argument("Invalid ANI percentage: " + preset + ". Use 50%-100% or 50-100");
+        ani = v;
+    }
+    if (ani >= 95.0) return "0,7,12,2,36,1";
+    if (ani >= 85.0) return "0,5,8,2,24,1";
+    if (ani >= 75.0) return "0,4,6,2,18,1";
+    if (ani >= 65.0) return "0,3,4,1";
+    return "0,1,1,1";
+}
+
+// -k / -e prefix filters (src/main.rs:237-277); returns the number of sequences removed
+inline size_t filter_by_prefixes(std::vector<Sequence>& seqs, const std::string& comma_list, bool keep) {
+    std::vector<std::string> prefixes;
+    size_t pos = 0;
+    while (pos <= comma_list.size()) {
+        size_t c = comma_list.find(',', pos);
+        if (c == std::string::npos) c = comma_list.size();
+        std::string s = comma_list.substr(pos, c - pos);
+        const size_t a = s.find_first_not_of(" \t"), b = s.find_last_not_of(" \t");
+        prefixes.push_back(a == std::string::npos ? std::string() : s.substr(a, b - a + 1));
+        pos = c + 1;
+    }
+    const size_t before = seqs.size();
+    seqs.erase(std::remove_if(seqs.begin(), seqs.end(),
+                              [&](const Sequence& s) {
+                                  bool any = false;
+                                  for (const auto& p : prefixes) any = any || s.id.compare(0, p.size(), p) == 0;
+                                  return keep ? !any : any;
+                              }),
+               seqs.end());
+    return before - seqs.size();
+}
+
+// --mash-matrix (src/main.rs:280-293, src/mash.rs:141-184): mash distances from the GPU sketches, printed like the reference
+inline void print_mash_matrix(Context& ctx, const std::vector<Sequence>& seqs, size_t kmer_size, FILE* out) {
+    const size_t n = seqs.size();
+    std::vector<uint32_t> inter(std::max<size_t>(1, n * n)), uni(std::max<size_t>(1, n * n));
+    if (n >= 1) {
+        int rc = aw_mash_jaccard_counts(ctx.get(), (int)kmer_size, 1000, inter.data(), uni.data());
+        if (rc != AW_OK) throw std::runtime_error(std::string("aw_mash_jaccard_counts: ") + aw_strerror(rc) + ": " + aw_last_error());
+    }
+    std::fputs("sequence", out);
+    for (const auto& s : seqs) std::fprintf(out, "\t%s", s.id.c_str());
+    std::fputc('\n', out);
+    for (size_t i = 0; i < n; ++i) {
+        std::fputs(seqs[i].id.c_str(), out);
+        for (size_t j = 0; j < n; ++j) std::fprintf(out, "\t%.6f", i == j ? 0.0 : mash_distance_from_counts(inter[i * n + j], uni[i * n + j], (int)kmer_size));
+        std::fputc('\n', out);
+    }
 }
 
 }  // namespace allwave

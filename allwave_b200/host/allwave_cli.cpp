@@ -1,7 +1,7 @@
 // allwave_cli.cpp -- minimal driver with allwave's CLI surface for the alignment path
-// (src/main.rs:32-80): -i FASTA [-o PAF] [-s scores] [-p strategy] [-t N] [--wfa-orientation]
-// [--no-progress] [--gpu D].  FASTA parsing and the PAF writer stay on the host; everything
-// between the pair list and the PAF text runs on the GPU through liballwave_cuda.so.
+// (src/main.rs:32-80): -i FASTA[.gz] [-o PAF] [-s scores | -x ANI preset] [-p strategy] [-t N] [-k prefixes | -e prefixes]
+// [--mash-matrix] [--wfa-orientation] [--no-progress] [--gpu D] [--gpus N].  FASTA parsing and the PAF writer stay on the
+// host; everything between the pair list and the PAF text runs on the GPU through liballwave_cuda.so.
 #include <chrono>
 #include <cstdio>
 #include <iostream>
@@ -10,8 +10,8 @@
 #include "allwave.hpp"
 
 int main(int argc, char** argv) {
-    std::string input, output, scores = "0,5,8,2,24,1", spars = "giant:0.99";
-    bool wfa_orientation = false, progress = true;
+    std::string input, output, scores = "0,5,8,2,24,1", spars = "giant:0.99", preset, keep_prefixes, exclude_prefixes;
+    bool wfa_orientation = false, progress = true, mash_matrix = false, scores_given = false;
     int device = 0, gpus = 1;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
@@ -24,7 +24,13 @@ int main(int argc, char** argv) {
         };
         if (a == "-i" || a == "--input") input = need("-i");
         else if (a == "-o" || a == "--output") output = need("-o");
-        else if (a == "-s" || a == "--scores") scores = need("-s");
+        else if (a == "-s" || a == "--scores") {
+            scores = need("-s");
+            scores_given = true;
+        } else if (a == "-x" || a == "--preset") preset = need("-x");
+        else if (a == "-k" || a == "--keep-prefixes") keep_prefixes = need("-k");
+        else if (a == "-e" || a == "--exclude-prefixes") exclude_prefixes = need("-e");
+        else if (a == "--mash-matrix") mash_matrix = true;
         else if (a == "-p" || a == "--sparsification") spars = need("-p");
         else if (a == "-t" || a == "--threads") (void)need("-t");  // host threads are irrelevant: pairs run on the GPU
         else if (a == "--gpu") device = std::atoi(need("--gpu").c_str());
@@ -32,9 +38,19 @@ int main(int argc, char** argv) {
         else if (a == "--wfa-orientation") wfa_orientation = true;
         else if (a == "--no-progress") progress = false;
         else {
-            std::fprintf(stderr, "usage: allwave -i FASTA [-o PAF] [-s scores] [-p none|auto|random:f|giant:p|tree:n:f:r[:k]] [--wfa-orientation] [--gpu D] [--gpus N]\n");
+            std::fprintf(stderr,
+                         "usage: allwave -i FASTA[.gz] [-o PAF] [-s scores | -x ANI] [-p none|auto|random:f|giant:p|tree:n:f:r[:k]] [-k prefixes | -e prefixes]\n"
+                         "               [--mash-matrix] [--wfa-orientation] [--no-progress] [--gpu D] [--gpus N]\n");
             return 2;
         }
+    }
+    if (!preset.empty() && scores_given) {  // clap: conflicts_with = "scores"
+        std::fprintf(stderr, "error: the argument '--preset <PRESET>' cannot be used with '--scores <SCORES>'\n");
+        return 2;
+    }
+    if (!keep_prefixes.empty() && !exclude_prefixes.empty()) {
+        std::fprintf(stderr, "error: the argument '--keep-prefixes <KEEP_PREFIXES>' cannot be used with '--exclude-prefixes <EXCLUDE_PREFIXES>'\n");
+        return 2;
     }
     if (input.empty()) {
         std::fprintf(stderr, "error: -i/--input is required\n");
@@ -42,11 +58,29 @@ int main(int argc, char** argv) {
     }
     try {
         using namespace allwave;
-        const AlignmentParams params = parse_scores(scores);
         const SparsificationStrategy sp = parse_sparsification(spars);
-        const std::vector<Sequence> seqs = read_fasta(input);
+        std::vector<Sequence> seqs = read_fasta(input);
+        if (!keep_prefixes.empty()) {
+            const size_t before = seqs.size(), removed = filter_by_prefixes(seqs, keep_prefixes, true);
+            if (removed) std::fprintf(stderr, "Kept sequences with prefixes: %zu -> %zu (prefixes: %s)\n", before, seqs.size(), keep_prefixes.c_str());
+            if (seqs.empty()) throw std::invalid_argument("No sequences match the specified keep prefixes");
+        }
+        if (!exclude_prefixes.empty()) {
+            const size_t before = seqs.size(), removed = filter_by_prefixes(seqs, exclude_prefixes, false);
+            if (removed) std::fprintf(stderr, "Excluded sequences with prefixes: %zu -> %zu (prefixes: %s)\n", before, seqs.size(), exclude_prefixes.c_str());
+            if (seqs.empty()) throw std::invalid_argument("All sequences were excluded by the specified prefixes");
+        }
         Context ctx(device);
         ctx.load(seqs);
+        if (mash_matrix) {  // src/main.rs:280-293: print the mash distance matrix and exit
+            print_mash_matrix(ctx, seqs, sp.kind == SparsificationStrategy::TreeSampling ? sp.kmer_size.value_or(15) : 15, stdout);
+            return 0;
+        }
+        if (!preset.empty()) {
+            scores = parse_ani_preset(preset);
+            std::fprintf(stderr, "Using ANI preset %s -> alignment scores: %s\n", preset.c_str(), scores.c_str());
+        }
+        const AlignmentParams params = parse_scores(scores);
         std::vector<std::unique_ptr<Context>> more;
         std::vector<Context*> others;
         for (int g = 1; g < gpus; ++g) {

@@ -115,5 +115,42 @@ int awh_partition_pairs(const uint64_t* pairs, uint64_t npairs, const uint64_t* 
     }
 }
 
+// parse_ani_preset (src/main.rs:83-124): writes the score string into out (>= 32 bytes)
+int awh_parse_ani_preset(const char* s, char* out) {
+    try {
+        const std::string r = parse_ani_preset(s);
+        std::strncpy(out, r.c_str(), 31);
+        out[31] = 0;
+        return 0;
+    } catch (const std::exception& e) {
+        g_msg = e.what();
+        return -1;
+    }
+}
+
+// read_fasta + the -k / -e prefix filters: returns the number of sequences, their ids joined by '\n' and their total length
+int64_t awh_read_fasta(const char* path, const char* keep, const char* exclude, char** ids_out, uint64_t* total_len) {
+    try {
+        std::vector<Sequence> seqs = read_fasta(path);
+        if (keep && *keep) filter_by_prefixes(seqs, keep, true);
+        if (exclude && *exclude) filter_by_prefixes(seqs, exclude, false);
+        std::string joined;
+        uint64_t tot = 0;
+        for (const auto& s : seqs) {
+            joined += s.id;
+            joined += '\n';
+            tot += s.seq.size();
+        }
+        char* o = (char*)std::malloc(joined.size() + 1);
+        std::memcpy(o, joined.c_str(), joined.size() + 1);
+        *ids_out = o;
+        *total_len = tot;
+        return (int64_t)seqs.size();
+    } catch (const std::exception& e) {
+        g_msg = e.what();
+        return -1;
+    }
+}
+
 void awh_free(void* p) { std::free(p); }
 }

@@ -33,6 +33,9 @@ def lib():
         L.awh_build_knn_graph.argtypes = [C.POINTER(C.c_double), C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
         L.awh_build_knn_graph.restype = C.POINTER(C.c_uint64)
         L.awh_free.argtypes = [C.c_void_p]
+        L.awh_parse_ani_preset.argtypes = [C.c_char_p, C.c_char_p]
+        L.awh_read_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.awh_read_fasta.restype = C.c_int64
         L.awh_partition_pairs.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
@@ -89,3 +92,23 @@ def partition_pairs(pairs, lens, n_parts):
     for i, p in enumerate(pairs):
         shards[out[i]].append(tuple(p))
     return shards
+
+
+def parse_ani_preset(s):
+    """parse_ani_preset of the reference CLI (src/main.rs:83-124)"""
+    buf = C.create_string_buffer(32)
+    if lib().awh_parse_ani_preset(s.encode(), buf) != 0:
+        raise ValueError(lib().awh_last_message().decode())
+    return buf.value.decode()
+
+
+def read_fasta(path, keep_prefixes="", exclude_prefixes=""):
+    """read_fasta (+ -k / -e prefix filters) of the C++ host: (ids, total sequence length); .gz input needs zlib"""
+    ids = C.c_void_p()
+    tot = C.c_uint64()
+    n = lib().awh_read_fasta(str(path).encode(), keep_prefixes.encode(), exclude_prefixes.encode(), C.byref(ids), C.byref(tot))
+    if n < 0:
+        raise RuntimeError(lib().awh_last_message().decode())
+    joined = C.string_at(ids.value).decode()
+    lib().awh_free(ids)
+    return [x for x in joined.split("\n") if x != ""][:n] if n else [], tot.value

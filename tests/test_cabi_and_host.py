@@ -178,3 +178,31 @@ def test_cpp_partition_matches_python():
         if parts > 1:
             loads = partition.shard_loads(got, lens)
             assert max(loads) <= 1.25 * (sum(loads) / parts) + max(partition.predicted_cost(lens[q], lens[t]) for q, t in pairs)
+
+
+def test_cli_surface_presets_filters_gz(tmp_path):
+    """the CLI rows of SURVEY 8(f): -x ANI presets (src/main.rs:83-124), -k / -e prefix filters (:237-277), .gz FASTA input"""
+    import gzip
+
+    from allwave_b200 import hostlib as H
+
+    for s, exp in [("98%", "0,7,12,2,36,1"), ("95", "0,7,12,2,36,1"), ("0.9", "0,5,8,2,24,1"), ("85%", "0,5,8,2,24,1"), ("80", "0,4,6,2,18,1"),
+                   ("0.7", "0,3,4,1"), ("60%", "0,1,1,1"), ("1.0", "0,7,12,2,36,1")]:
+        assert H.parse_ani_preset(s) == exp
+    for bad in ("40%", "101", "1.5", "abc", "0.0", ""):
+        with pytest.raises(ValueError):
+            H.parse_ani_preset(bad)
+    recs = [("sampleA#1#chr1 desc", "ACGTACGTAC"), ("sampleA#2#chr1", "ACGT\nACGT"), ("sampleB#1#chr1", "GGGG"), ("other", "TT")]
+    text = "".join(f">{i}\n{s}\n" for i, s in recs)
+    fa = tmp_path / "x.fa"
+    fa.write_text(text)
+    ids, tot = H.read_fasta(fa)
+    assert ids == ["sampleA#1#chr1", "sampleA#2#chr1", "sampleB#1#chr1", "other"] and tot == 10 + 8 + 4 + 2
+    assert H.read_fasta(fa, keep_prefixes="sampleA, other")[0] == ["sampleA#1#chr1", "sampleA#2#chr1", "other"]
+    assert H.read_fasta(fa, exclude_prefixes="sampleA#1,sampleB")[0] == ["sampleA#2#chr1", "other"]
+    gz = tmp_path / "x.fa.gz"
+    with gzip.open(gz, "wb") as f:  # two gzip members back to back, like bgzf blocks
+        f.write(text[:30].encode())
+    with open(gz, "ab") as f:
+        f.write(gzip.compress(text[30:].encode()))
+    assert H.read_fasta(gz) == (ids, tot)

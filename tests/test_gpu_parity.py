@@ -283,3 +283,36 @@ def test_cli_multi_gpu_matches_single(tmp_path):
         subprocess.check_call([exe, "-i", str(fa), "-o", str(out), "-p", "none", "--no-progress", "--gpus", str(g)])
         outs.append(sorted(out.read_text().splitlines()))
     assert len(outs[0]) == 24 * 23 and outs[0] == outs[1]
+
+
+def test_cli_mash_matrix_and_preset(oracle, gpu_ctx, tmp_path):
+    """--mash-matrix prints the reference's tab-separated distance table (src/mash.rs:168-184) from the GPU sketches;
+    -x 90% aligns with the preset's scores; gzipped input"""
+    import gzip
+    import math
+    import subprocess
+
+    c, ids, seqs, rc = synth.config("C5", n=5, length=2500)
+    fa = tmp_path / "in.fa.gz"
+    with gzip.open(fa, "wt") as f:
+        f.write("".join(f">{i}\n{s.decode()}\n" for i, s in zip(ids, seqs)))
+    exe = os.path.join(os.path.dirname(aw._cabi.so_path()), "allwave")
+    out = subprocess.run([exe, "-i", str(fa), "--mash-matrix"], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0].split("\t") == ["sequence"] + ids and len(out) == 6
+    for i in range(5):
+        row = out[1 + i].split("\t")
+        assert row[0] == ids[i]
+        for j in range(5):
+            if i == j:
+                exp = 0.0
+            else:
+                inter, uni = oracle.jaccard_counts(oracle.sketch(seqs[i], canonical=True), oracle.sketch(seqs[j], canonical=True))
+                jac = inter / uni if uni else 0.0
+                exp = 1.0 if jac <= 0.0 else (-1.0 / 15.0) * math.log(2.0 * jac / (1.0 + jac))
+            assert row[1 + j] == f"{exp:.6f}"
+    paf = tmp_path / "o.paf"
+    subprocess.check_call([exe, "-i", str(fa), "-o", str(paf), "-p", "none", "-x", "90%", "--no-progress", "-e", ids[4]])
+    lines = paf.read_text().splitlines()
+    p = oracle.params(**DEFAULT)
+    want = [oracle.align_pair(seqs[q], seqs[t], q, t, p, use_mash=True, qname=ids[q], tname=ids[t])["paf"] for q, t in _all_pairs(4)]
+    assert lines == want
