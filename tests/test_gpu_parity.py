@@ -316,3 +316,28 @@ def test_cli_mash_matrix_and_preset(oracle, gpu_ctx, tmp_path):
     p = oracle.params(**DEFAULT)
     want = [oracle.align_pair(seqs[q], seqs[t], q, t, p, use_mash=True, qname=ids[q], tname=ids[t])["paf"] for q, t in _all_pairs(4)]
     assert lines == want
+
+
+def test_golden_fixtures_gpu(gpu_ctx):
+    """the CUDA path against the committed golden fixtures (tests/golden/oracle_golden.json): the four published /
+    hand-derived anchors and the 132 frozen alignments (score, strand, whole PAF line)"""
+    import json
+
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_golden.json")))
+    pens = {"affine2p": DEFAULT, "edit": EDIT, "affine": AFFINE}
+    for a in gold["anchors"]:
+        gpu_ctx.load_sequences(["q", "t"], [a["q"].encode(), a["t"].encode()])
+        r = gpu_ctx.align_pairs(aw.make_params(**pens[a["pen"]]), [(0, 1)], orientation=aw.AW_ORIENT_FORWARD, flags=aw.AW_FLAG_CIGAR_BYTES)[0]
+        assert (r["score"], r["cigar_bytes"].decode(), r["cg"]) == (a["score"], a["ops"], a["cg"]), a["src"]
+    groups = {}
+    for g in gold["alignments"]:
+        groups.setdefault((g["seed"], g["n"], g["length"], g["d"], g["rc_prob"], g["pen"]), []).append(g)
+    checked = 0
+    for (seed, n, length, d, rcp, pen), items in groups.items():
+        ids, seqs, _ = synth.generate(seed, n, length, d, rc_prob=rcp)
+        gpu_ctx.load_sequences(ids, seqs)
+        res = gpu_ctx.align_pairs(aw.make_params(**pens[pen]), [(g["q"], g["t"]) for g in items], orientation=aw.AW_ORIENT_MASH)
+        for r, g in zip(res, items):
+            assert (r["score"], int(r["is_reverse"]), r["paf"]) == (g["score"], g["is_reverse"], g["paf"]), (g["case"], pen, g["q"], g["t"])
+            checked += 1
+    assert checked == len(gold["alignments"]) == 132
