@@ -341,3 +341,23 @@ def test_golden_fixtures_gpu(gpu_ctx):
             assert (r["score"], int(r["is_reverse"]), r["paf"]) == (g["score"], g["is_reverse"], g["paf"]), (g["case"], pen, g["q"], g["t"])
             checked += 1
     assert checked == len(gold["alignments"]) == 132
+
+
+def test_retry_ladder_small_workspace(oracle):
+    """pairs whose wavefronts outgrow the first-try workspace (capped width, tiny history arena) report AW_EWORKSPACE on the
+    device and are re-run by the host with larger workspaces; the results must not change"""
+    ids, seqs, _ = synth.generate(77, 4, 3000, 0.08)
+    pairs = _all_pairs(4)
+    for opts in (dict(max_wavefront_width=256), dict(hist_mb=1, max_wavefront_width=512), dict(max_wavefront_width=128, threads_per_cta=256, ws16=0)):
+        ctx = aw.Context(0)
+        try:
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            _compare(oracle, ctx, ids, seqs, pairs, DEFAULT)
+            b = aw.Batch(ctx, aw.make_params(**DEFAULT), pairs, flags=0)
+            b.launch()
+            b.fetch(collect=False)
+            assert b.stats()["pairs_retried"] > 0 and b.stats()["failed_pairs"] == 0, opts
+            b.close()
+        finally:
+            ctx.close()
