@@ -83,10 +83,23 @@ int main(int argc, char** argv) {
         const AlignmentParams params = parse_scores(scores);
         std::vector<std::unique_ptr<Context>> more;
         std::vector<Context*> others;
-        for (int g = 1; g < gpus; ++g) {
-            more.emplace_back(new Context(device + g));
-            more.back()->load(seqs);
-            others.push_back(more.back().get());
+        {  // the other GPUs' contexts are created and loaded concurrently (CUDA context creation takes seconds per device)
+            more.resize(gpus > 1 ? gpus - 1 : 0);
+            std::vector<std::thread> th;
+            std::vector<std::exception_ptr> errs(more.size());
+            for (size_t g = 0; g < more.size(); ++g)
+                th.emplace_back([&, g] {
+                    try {
+                        more[g].reset(new Context(device + 1 + (int)g));
+                        more[g]->load(seqs);
+                    } catch (...) {
+                        errs[g] = std::current_exception();
+                    }
+                });
+            for (auto& t : th) t.join();
+            for (auto& e : errs)
+                if (e) std::rethrow_exception(e);
+            for (auto& m : more) others.push_back(m.get());
         }
         AllPairIterator it(ctx, seqs, params, true, !wfa_orientation, sp);
         FILE* out = output.empty() ? stdout : std::fopen(output.c_str(), "w");
