@@ -728,9 +728,11 @@ cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bo
     AW_CASE(256, 8, true, short, true)
     AW_CASE(256, 8, false, short, true)
     AW_CASE(128, 2, false, short, true)
+    AW_CASE(128, 2, false, int, false)
 #endif
     AW_CASE(256, 2, true, short, true)
     AW_CASE(128, 2, true, short, true)
+    AW_CASE(128, 2, true, int, false)
 #undef AW_CASE
     return cudaErrorInvalidValue;
 }
@@ -742,9 +744,10 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     const uint64_t maxlen = std::max(max_p, max_t);
     // int16 storage: every offset (incl. out-of-bounds I/D drift, <= 2*tlen+plen) must stay below 32000
     const bool fits16 = c->ws16 && (2 * max_t + max_p < 32000) && (2 * max_p + max_t < 32000);
-    // pairs up to 1 kb: one warp per pair; int16-sized pairs on 2-bit sequences: 128 threads (2 warps per direction,
-    // 4 CTAs per SM measured best on C2); everything else: 256 threads
-    int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : ((fits16 && c->all_clean) ? 128 : 256));
+    // pairs up to 1 kb: one warp per pair; 2-bit pairs up to 50 kb: 128 threads (2 warps per direction, 4 CTAs per SM
+    // measured best on C2); everything else: 256 threads
+    // (20 kb pairs, int32 rows: 571 pairs/s with 128 threads vs 501 with 256); Mb-scale pairs keep 256 threads per pair
+    int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : ((c->all_clean && (fits16 || maxlen <= 50000)) ? 128 : 256));
     int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : AW_CTAS_PER_SM(nt));
     uint64_t full_w = (max_p + max_t + 3 + 16 + 15) & ~15ull;  // rows are 16-element aligned (vectorised int16 loop)
     uint64_t W = full_w;
@@ -753,7 +756,7 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     for (int a = 0; a < attempt; ++a) hist_ints *= 8;
     int hist_max_scores = attempt == 0 ? (nt == 32 ? 1024 : 4096) : (attempt == 1 ? 32768 : 262144);
     uint64_t runs_cap = max_p + max_t + 4;
-    if (nt == 128 && !(fits16 && c->all_clean)) nt = 256;  // the 128-thread kernels exist for the int16 2-bit path only
+    if (nt == 128 && !c->all_clean) nt = 256;  // the 128-thread kernels exist for the chunked 2-bit path only
     const bool ws16 = fits16 && nt >= 64;
     const uint64_t epi = ws16 ? 2 : 1;  // elements per int
     // + the all-NULL row and the compact I/D rings of the int16 path (aw_wfa.cuh: null_base, cmp_base)
