@@ -702,7 +702,23 @@ struct LaunchCfg {
 template <int NT, int BITS, bool TWO, class WS>
 cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStream_t st) {
     auto kern = awk::aw_align_kernel<NT, BITS, TWO, WS>;
-    if (smem > 40 * 1024) {
+    // static + dynamic shared memory together decide whether the opt-in is needed (the kernels carry up to 28 KB of static
+    // shared memory); query the static part once per instantiation
+    static size_t static_smem = ~(size_t)0;
+    static int max_optin = 0;
+    if (static_smem == ~(size_t)0) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        static_smem = fa.sharedSizeBytes;
+    }
+    // int16 2-bit kernels read the staged sequences through a 32 KB address window (ld16s): the CTA must own all of it
+    if (NT >= 64 && BITS == 2 && sizeof(WS) == 2 && static_smem + smem < awk::SEQ2_WINDOW) smem = awk::SEQ2_WINDOW - static_smem;
+    if (static_smem + smem > (size_t)max_optin) return cudaErrorInvalidConfiguration;
+    if (static_smem + smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
@@ -743,7 +759,8 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     const int ncomp = pen.two_piece ? 5 : 3;
     const uint64_t maxlen = std::max(max_p, max_t);
     // int16 storage: every offset (incl. out-of-bounds I/D drift, <= 2*tlen+plen) must stay below 32000
-    const bool fits16 = c->ws16 && (2 * max_t + max_p < 32000) && (2 * max_p + max_t < 32000);
+    // ... and a (drifted) null must stay separable from every real antidiagonal: 3 * (plen + tlen) < 63000 (aw_wfa.cuh, wf_cells_v)
+    const bool fits16 = c->ws16 && (2 * max_t + max_p < 32000) && (2 * max_p + max_t < 32000) && (3 * (max_p + max_t) < 63000);
     // pairs up to 1 kb: one warp per pair; 2-bit pairs up to 50 kb: 128 threads (2 warps per direction, 4 CTAs per SM
     // measured best on C2); everything else: 256 threads
     // (20 kb pairs, int32 rows: 571 pairs/s with 128 threads vs 501 with 256); Mb-scale pairs keep 256 threads per pair

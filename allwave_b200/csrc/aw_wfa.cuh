@@ -388,6 +388,16 @@ __device__ __forceinline__ uint32_t load16(const uint2* __restrict__ s2, int pos
     const uint2 e = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(s2) + (((unsigned)pos >> 1) & ~7u));
     return __funnelshift_r(e.x, e.y, pos << 1);
 }
+// The same 16-symbol window from an array staged in SHARED memory, addressed by q = 2 * position + 4 * (byte address of the
+// array in the CTA's shared window): byte address = (q >> 2) & ~7, funnel shift = q mod 32.  The address is confined to the
+// first 32 KB of the window, so any q (null or out-of-bounds cells) reads legal memory; the caller discards such results.
+constexpr unsigned SEQ2_WINDOW = 32768;
+__device__ __forceinline__ uint32_t ld16s(int q) {
+    const uint32_t a = ((uint32_t)q >> 2) & (SEQ2_WINDOW - 8);
+    uint32_t lo, hi;
+    asm("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(a));
+    return __funnelshift_r(lo, hi, q);
+}
 // matching symbols from (pp, tp), at most maxlen
 __device__ __forceinline__ int lcp2(const uint2* __restrict__ p2, const uint2* __restrict__ t2, int pp, int tp, int maxlen) {
     int n = 0;
@@ -514,6 +524,12 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
     static_assert(BITS == 2, "the chunked path reads 2-bit sequences");
     using T = VecT<WS>;
     constexpr int CPT = 4 * T::CPW;
+    constexpr bool SSEQ = sizeof(WS) == 2;  // int16 rows <=> the sequences are staged in shared memory (SEQ_SMEM)
+    // ld16s() takes 2 * position + 4 * (shared-window byte address of the staged array)
+    int cq_p = SSEQ ? 2 * s_p0 + 4 * (int)__cvta_generic_to_shared(s_p2) : 0;
+    int cq_t = SSEQ ? 2 * s_t0 + 4 * (int)__cvta_generic_to_shared(s_t2) : 0;
+    asm volatile("" : "+r"(cq_p), "+r"(cq_t));  // opaque: keeps ptxas from re-deriving them per cell (3 instructions instead of 1)
+    const int ak_null = -(s_tlen + 8);
     // pf_off: lanes IN_MO1 / IN_MO2 hold the element offset of the M row those inputs will be two steps from now
     // (or -1): rows that old have usually left L2, so their lines are requested now (prefetch.global.L2)
     int pf1 = -1, pf2 = -1;
@@ -525,69 +541,75 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
     constexpr int SH = (CPT == 8) ? 3 : 2;
     constexpr int OWN = VBLOCK_CHUNKS;  // chunks owned per warp iteration (lanes 1..30)
     const int lane = threadIdx.x & 31;
-    const int o_mx = __shfl_sync(0xffffffffu, in_off, IN_MX), o_mo1 = __shfl_sync(0xffffffffu, in_off, IN_MO1);
-    const int o_i1e = __shfl_sync(0xffffffffu, in_off, IN_I1E), o_d1e = __shfl_sync(0xffffffffu, in_off, IN_D1E);
+    // Row addressing.  int16 rows: offsets are kept in BYTES and added to the workspace base as one unsigned 32-bit value
+    // (IADD + 64-bit add = 3 instructions per access instead of 4 with sign extension and scaling; a CTA's int16 workspace is
+    // below 4 GB).  int32 rows (Mb-scale pairs) keep element offsets and 64-bit pointer arithmetic.
+    constexpr int OS = SSEQ ? 2 : 1;
+    auto at = [&](int kc_, int o) -> WS* {
+        if constexpr (SSEQ) return reinterpret_cast<WS*>(reinterpret_cast<char*>(ws) + (uint32_t)(((uint32_t)kc_ << 1) + (uint32_t)o));
+        else return ws + kc_ + o;
+    };
+    const int o_mx = OS * __shfl_sync(0xffffffffu, in_off, IN_MX), o_mo1 = OS * __shfl_sync(0xffffffffu, in_off, IN_MO1);
+    const int o_i1e = OS * __shfl_sync(0xffffffffu, in_off, IN_I1E), o_d1e = OS * __shfl_sync(0xffffffffu, in_off, IN_D1E);
     int o_mo2 = 0, o_i2e = 0, o_d2e = 0;
     if (TWO) {
-        o_mo2 = __shfl_sync(0xffffffffu, in_off, IN_MO2);
-        o_i2e = __shfl_sync(0xffffffffu, in_off, IN_I2E);
-        o_d2e = __shfl_sync(0xffffffffu, in_off, IN_D2E);
+        o_mo2 = OS * __shfl_sync(0xffffffffu, in_off, IN_MO2);
+        o_i2e = OS * __shfl_sync(0xffffffffu, in_off, IN_I2E);
+        o_d2e = OS * __shfl_sync(0xffffffffu, in_off, IN_D2E);
     }
     const int c_lo = lo >> SH, c_hi = hi >> SH;  // arithmetic shift = floor
-    const int o_m = ocoff[AW_COMP_M], o_i1 = ocoff[AW_COMP_I1], o_i2 = ocoff[AW_COMP_I2], o_d1 = ocoff[AW_COMP_D1], o_d2 = ocoff[AW_COMP_D2];
+    const int o_m = OS * ocoff[AW_COMP_M], o_i1 = OS * ocoff[AW_COMP_I1], o_i2 = OS * ocoff[AW_COMP_I2], o_d1 = OS * ocoff[AW_COMP_D1], o_d2 = OS * ocoff[AW_COMP_D2];
     int akM = INT_MIN, akAll = INT_MIN;
     bool oob = false;
     int bidx = gwarp;
     for (int cw = c_lo + gwarp * OWN; cw <= c_hi; cw += gnw * OWN, bidx += gnw) {
         int akM_b = INT_MIN, akAll_b = INT_MIN;
-        const int c = cw - 1 + lane;
+        // lanes past the right halo chunk (c_hi + 1) feed nobody: they shadow the halo lane (same addresses, one request per
+        // warp) instead of taking a branch of their own with 20 NULL-initialised registers
+        const int c = min(cw - 1 + lane, c_hi + 1);
         const int kc = c << SH;
-        const bool own = (lane >= 1) && (lane <= OWN) && (c <= c_hi);
+        const bool own = (lane >= 1) && (lane <= OWN) && (cw - 1 + lane <= c_hi);
         const bool fast = (kc >= fast_lo) && (kc + CPT - 1 <= fast_hi);
         uint32_t mx[VW], tI1[VW], tD1[VW], tI2[VW], tD2[VW];
-        if (c > c_hi + 1) {  // neither owned nor a neighbour's halo
-#pragma unroll
-            for (int i = 0; i < VW; ++i) mx[i] = tI1[i] = tD1[i] = tI2[i] = tD2[i] = T::NULLW;
-        } else {
+        {
             uint32_t mo[VW], ie[VW], de[VW], mo2[VW], ie2[VW], de2[VW];
             if (fast) {
-                const WS* pk = ws + kc;
                 if (AW_PREFETCH_STEPS > 0) {
-                    if (pf1 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + pf1));
-                    if (pf2 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pk + pf2));
+                    if (pf1 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(at(kc, OS * pf1)));
+                    if (pf2 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(at(kc, OS * pf2)));
                 }
-                ld_vec<WS>(pk + o_mx, mx);
-                ld_vec<WS>(pk + o_mo1, mo);
-                ld_vec<WS>(pk + o_i1e, ie);
-                ld_vec<WS>(pk + o_d1e, de);
+                ld_vec<WS>(at(kc, o_mx), mx);
+                ld_vec<WS>(at(kc, o_mo1), mo);
+                ld_vec<WS>(at(kc, o_i1e), ie);
+                ld_vec<WS>(at(kc, o_d1e), de);
                 if (TWO) {
-                    ld_vec<WS>(pk + o_mo2, mo2);
-                    ld_vec<WS>(pk + o_i2e, ie2);
-                    ld_vec<WS>(pk + o_d2e, de2);
+                    ld_vec<WS>(at(kc, o_mo2), mo2);
+                    ld_vec<WS>(at(kc, o_i2e), ie2);
+                    ld_vec<WS>(at(kc, o_d2e), de2);
                 }
                 if (AW_PREFETCH_NEXT_ITER && cw + gnw * OWN <= c_hi) {
                     // this warp's next iteration reads the same rows gnw*OWN chunks further on: request those lines now so that
                     // only the first iteration of a step waits for L2 / HBM
-                    const WS* pn = pk + gnw * OWN * CPT;
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_mx));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_mo1));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_i1e));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_d1e));
+                    const int kn = kc + gnw * OWN * CPT;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_mx)));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_mo1)));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_i1e)));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_d1e)));
                     if (TWO) {
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_mo2));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_i2e));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + o_d2e));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_mo2)));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_i2e)));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_d2e)));
                     }
                 }
             } else {
-                load_row<WS>(ws, o_mx, dsc[IN_MX], dsc[8 + IN_MX], kc, mx);
-                load_row<WS>(ws, o_mo1, dsc[IN_MO1], dsc[8 + IN_MO1], kc, mo);
-                load_row<WS>(ws, o_i1e, dsc[IN_I1E], dsc[8 + IN_I1E], kc, ie);
-                load_row<WS>(ws, o_d1e, dsc[IN_D1E], dsc[8 + IN_D1E], kc, de);
+                load_row<WS>(ws, o_mx / OS, dsc[IN_MX], dsc[8 + IN_MX], kc, mx);
+                load_row<WS>(ws, o_mo1 / OS, dsc[IN_MO1], dsc[8 + IN_MO1], kc, mo);
+                load_row<WS>(ws, o_i1e / OS, dsc[IN_I1E], dsc[8 + IN_I1E], kc, ie);
+                load_row<WS>(ws, o_d1e / OS, dsc[IN_D1E], dsc[8 + IN_D1E], kc, de);
                 if (TWO) {
-                    load_row<WS>(ws, o_mo2, dsc[IN_MO2], dsc[8 + IN_MO2], kc, mo2);
-                    load_row<WS>(ws, o_i2e, dsc[IN_I2E], dsc[8 + IN_I2E], kc, ie2);
-                    load_row<WS>(ws, o_d2e, dsc[IN_D2E], dsc[8 + IN_D2E], kc, de2);
+                    load_row<WS>(ws, o_mo2 / OS, dsc[IN_MO2], dsc[8 + IN_MO2], kc, mo2);
+                    load_row<WS>(ws, o_i2e / OS, dsc[IN_I2E], dsc[8 + IN_I2E], kc, ie2);
+                    load_row<WS>(ws, o_d2e / OS, dsc[IN_D2E], dsc[8 + IN_D2E], kc, de2);
                 }
             }
 #pragma unroll
@@ -625,16 +647,25 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
                 }
                 vM[i] = m;
             }
-            WS* pk = ws + kc;
-            st_vec<WS>(pk + o_i1, vI1);
-            st_vec<WS>(pk + o_d1, vD1);
+            st_vec<WS>(at(kc, o_i1), vI1);
+            st_vec<WS>(at(kc, o_d1), vD1);
             if (TWO) {
-                st_vec<WS>(pk + o_i2, vI2);
-                st_vec<WS>(pk + o_d2, vD2);
+                st_vec<WS>(at(kc, o_i2), vI2);
+                st_vec<WS>(at(kc, o_d2), vD2);
             }
             if (comp_end != AW_COMP_M && k_end >= kc && k_end < kc + CPT) {
+                // select the VALUES, never a pointer to one of the register arrays: a pointer select forces all four
+                // arrays into local memory on every iteration (16 STL per chunk, 2.4x the kernel's global stores in r01)
                 const int j = k_end - kc;
-                const uint32_t* src = (comp_end == AW_COMP_I1) ? vI1 : (comp_end == AW_COMP_D1) ? vD1 : (comp_end == AW_COMP_I2) ? vI2 : vD2;
+                uint32_t src[VW];
+#pragma unroll
+                for (int i = 0; i < VW; ++i) {
+                    uint32_t w = vI1[i];
+                    if (comp_end == AW_COMP_D1) w = vD1[i];
+                    if (TWO && comp_end == AW_COMP_I2) w = vI2[i];
+                    if (TWO && comp_end == AW_COMP_D2) w = vD2[i];
+                    src[i] = w;
+                }
                 int val = T::get(src, 0);
 #pragma unroll
                 for (int q = 1; q < CPT; ++q)
@@ -647,6 +678,36 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
             int mm[CPT];
             unsigned more = 0;
             int oobm = 0;
+            if constexpr (SSEQ) {
+                // int16 rows + sequences in shared memory.  ~33 instructions per cell instead of 58:
+                //  * the two sequence reads are not masked for invalid cells: the address is confined to the first 32 KB of the
+                //    CTA's shared window (which holds the staged sequences, see the kernel prologue), so a null or out-of-bounds
+                //    cell reads harmless garbage that the validity select discards;
+                //  * nulls are <= NULL16 + drift, so 2*m - k of a null cell is far below every real antidiagonal and needs no mask
+                //    (normalised to INT_MIN once per warp iteration);
+                //  * "whole word matched and symbols remain" is folded into one running maximum, resolved per cell only when it fires.
+                int zmax = 0;
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) {
+                    const int m = T::get(vM, j);
+                    const int v = m - kc - j;
+                    const int maxlen = min(s_plen - v, s_tlen - m);
+                    const int w = m | v | maxlen;          // sign bit clear iff 0 <= h <= tlen and 0 <= v <= plen
+                    const bool valid = w >= 0;
+                    oobm |= ~m & w;                        // sign bit: a non-null offset outside the sequences
+                    akAll_b = max(akAll_b, m + v);         // 2*off - k; m (pre-null) dominates every component at k
+                    const uint32_t x = ld16s(2 * v + cq_p) ^ ld16s(2 * m + cq_t);
+                    const int cnt = __clz(__brev(x)) >> 1;  // matching symbols = trailing zero pairs; 16 when the whole word matches
+                    const int ml = valid ? maxlen : 0;
+                    zmax = max(zmax, min(ml - 1, cnt));    // 16 iff the whole word matched and symbols remain
+                    mm[j] = valid ? m + min(cnt, ml) : T::NULLV;
+                }
+                oobm >>= 31;
+                if (zmax >= 16) {
+#pragma unroll
+                    for (int j = 0; j < CPT; ++j) more |= (unsigned)((mm[j] >= 0) && (mm[j] - T::get(vM, j) == 16)) << j;
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
                 const int k = kc + j;
@@ -664,6 +725,7 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
                 mm[j] = ((m + ext) & vmask) | (T::NULLV & ~vmask);
                 more |= (unsigned)((cnt >> 4) & ((16 - maxlen) >> 31) & vmask & 1) << j;  // whole word matched and symbols remain
             }
+            }
             oob = oob || (oobm != 0);
             while (more) {  // long match runs: continue word by word, one cell at a time (kept small: instruction-cache footprint)
                 const int j = __ffs(more) - 1;
@@ -680,8 +742,12 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
             }
 #pragma unroll
             for (int j = 0; j < CPT; ++j) {
-                const int nonneg = ~(mm[j] >> 31);
-                akM_b = max(akM_b, ((2 * mm[j] - (kc + j)) & nonneg) | (INT_MIN & ~nonneg));
+                if constexpr (SSEQ) {
+                    akM_b = max(akM_b, mm[j] + (mm[j] - kc - j));  // a null cell lands far below every real antidiagonal
+                } else {
+                    const int nonneg = ~(mm[j] >> 31);
+                    akM_b = max(akM_b, ((2 * mm[j] - (kc + j)) & nonneg) | (INT_MIN & ~nonneg));
+                }
             }
             if (comp_end == AW_COMP_M && k_end >= kc && k_end < kc + CPT) {
                 const int j = k_end - kc;
@@ -696,7 +762,7 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
                 if constexpr (T::CPW == 2) vM[i] = __byte_perm((uint32_t)mm[2 * i], (uint32_t)mm[2 * i + 1], 0x5410);
                 else vM[i] = (uint32_t)mm[i];
             }
-            st_vec<WS>(pk + o_m, vM);
+            st_vec<WS>(at(kc, o_m), vM);
         }
         if (AW_L1_PREFETCH && own) {  // the next step reads the same diagonals of these rows: pull their lines into L1 now
 #pragma unroll
@@ -704,6 +770,12 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
                 const int o = dsc[24 + i];
                 if (o >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(ws + kc + o));
             }
+        }
+        if constexpr (SSEQ) {
+            // 2*off - k of a (possibly drifted) null is below -(tlen + 8): NULL16 + drift <= -32000 + plen + tlen + 100 and
+            // plan_launch only selects int16 rows when 3 * (plen + tlen) < 63000
+            if (akM_b < ak_null) akM_b = INT_MIN;
+            if (akAll_b < ak_null) akAll_b = INT_MIN;
         }
         if (blk != nullptr) {
             akM_b = __reduce_max_sync(0xffffffffu, akM_b);
@@ -928,6 +1000,11 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     uint32_t* const pair_runs = P.ws_runs + (size_t)blockIdx.x * 2 * P.runs_cap;
     uint32_t* const leaf_runs = pair_runs + P.runs_cap;
 
+    if constexpr (SEQ_SMEM) {
+        // ld16s() confines its addresses to the first SEQ2_WINDOW bytes of the shared window: the staged sequences must lie
+        // inside (launch_align pads the dynamic part so that the CTA owns at least that much)
+        if (tid == 0 && __cvta_generic_to_shared(s_seq2) + sizeof(s_seq2) > SEQ2_WINDOW) __trap();
+    }
     for (int i = tid; i < 2 * 3 * NRED; i += NT) (&red[0][0][0])[i] = INT_MIN;
     if constexpr (VEC) {
         const uint4 nv = make_uint4(VecT<WS>::NULLW, VecT<WS>::NULLW, VecT<WS>::NULLW, VecT<WS>::NULLW);
@@ -1792,7 +1869,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 // ---- phase 2: advance until no better breakpoint is possible ----
                 // Half-steps: the direction that stepped last acts as aligner 0 of wavefront_bialign_overlap, then the other
                 // direction steps (one overlap / one step call site: instruction-cache footprint).
-                const int gap_opening = TWO ? pen.o2 : pen.o1;
+                const int gap_opening = AW_BIALIGN_GAP_OPENING(TWO, pen.o1, pen.o2);
                 int a0 = last_forward ? 0 : 1;
                 while (!fb_end && status == ST_OK) {
                     const int d0 = a0, d1 = 1 - a0;

@@ -28,6 +28,12 @@
 #define AW_BIALIGN_PHASE1_END_REACHED_RETURNS 1
 #define AW_BIALIGN_PHASE2_END_REACHED_RETURNS 0
 
+/* wavefront_bialign_find_breakpoint, overlap phase: the search stops once
+ * score_0 + min_score_1 - gap_opening >= breakpoint.score, where gap_opening is the largest gap-opening
+ * credit an indel-to-indel meeting can earn (SURVEY.md A.5 `gap_open_max`): o1 for gap-affine,
+ * max(o1, o2) for gap-affine-2p. */
+#define AW_BIALIGN_GAP_OPENING(two_piece, o1, o2) ((two_piece) ? ((o1) > (o2) ? (o1) : (o2)) : (o1))
+
 /* wavefront_compute_process_ends: trim the [lo,hi] of every output component (1) or of M only (0) */
 #define AW_TRIM_ALL_COMPONENTS 1
 

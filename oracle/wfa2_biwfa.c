@@ -589,7 +589,7 @@ static int bialign_find_breakpoint(bialigner_t* b, const uint8_t* p, int plen, c
         if ((int64_t)score_f + score_r > step_limit) return ST_ERROR;
     }
     const int scope = f->scope;
-    const int gap_opening = f->pen.two_piece ? f->pen.o2 : f->pen.o1;
+    const int gap_opening = AW_BIALIGN_GAP_OPENING(f->pen.two_piece, f->pen.o1, f->pen.o2);
     for (;;) {
         if (last_forward) {
             const int min_r = (score_r > scope - 1) ? score_r - (scope - 1) : 0;
