@@ -14,7 +14,7 @@ _SO = os.path.join(_PKG, "liballwave_cuda.so")
 AW_OK = 0
 AW_EINVAL, AW_ENODEVICE, AW_ECUDA, AW_ENOMEM, AW_EUNSUPPORTED, AW_EWORKSPACE, AW_ECALLBACK, AW_EALIGN = -1, -2, -3, -4, -5, -6, -7, -8
 AW_ORIENT_MASH, AW_ORIENT_WFA, AW_ORIENT_FORWARD = 0, 1, 2
-AW_FLAG_CIGAR_BYTES, AW_FLAG_ORDERED, AW_FLAG_NO_PAF = 1, 2, 4
+AW_FLAG_CIGAR_BYTES, AW_FLAG_ORDERED, AW_FLAG_NO_PAF, AW_FLAG_PAF_BLOCKS = 1, 2, 4, 8
 AW_MEMORY_HIGH, AW_MEMORY_MEDIUM, AW_MEMORY_LOW, AW_MEMORY_ULTRALOW = 0, 1, 2, 3
 
 EXPORTS = [
@@ -23,7 +23,7 @@ EXPORTS = [
     "aw_batch_stats", "aw_batch_kernel_ms", "aw_batch_debug_cycles", "aw_batch_destroy", "aw_orient_pairs", "aw_get_sketch", "aw_mash_jaccard_counts",
     "aw_aligner_new_affine", "aw_aligner_new_affine2p", "aw_aligner_set_alignment_scope", "aw_aligner_set_alignment_span",
     "aw_aligner_set_heuristic", "aw_aligner_get_memory_mode", "aw_aligner_align", "aw_aligner_score", "aw_aligner_cigar",
-    "aw_aligner_delete",
+    "aw_aligner_delete", "aw_align_stream", "aw_estimate_divergence", "aw_trim_cache",
 ]
 
 
@@ -67,6 +67,8 @@ class AwResult(C.Structure):
 
 
 RESULT_CB = C.CFUNCTYPE(C.c_int, C.POINTER(AwResult), C.c_void_p)
+CHUNK_SOURCE = C.CFUNCTYPE(C.c_uint64, C.c_void_p, C.POINTER(C.POINTER(AwPair)))
+PAF_BLOCK_CB = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_char), C.c_uint64, C.c_uint64, C.c_void_p)
 
 _lib = None
 
@@ -114,6 +116,9 @@ def lib():
     L.aw_num_sequences.restype = C.c_uint32
     L.aw_set_orientation_params.argtypes = [vp, C.POINTER(AwParams)]
     L.aw_align_pairs.argtypes = [vp, C.POINTER(AwParams), C.c_int, C.POINTER(AwPair), C.c_uint64, C.c_uint32, RESULT_CB, vp]
+    L.aw_align_stream.argtypes = [vp, C.POINTER(AwParams), C.c_int, C.c_uint32, CHUNK_SOURCE, vp, RESULT_CB, PAF_BLOCK_CB, vp]
+    L.aw_estimate_divergence.argtypes = [vp, C.POINTER(AwPair), C.c_uint64, C.POINTER(C.c_float)]
+    L.aw_trim_cache.restype = None
     L.aw_batch_create.argtypes = [vp, C.POINTER(AwParams), C.c_int, C.POINTER(AwPair), C.c_uint64, C.c_uint32, C.POINTER(vp)]
     L.aw_batch_launch.argtypes = [vp, vp, vp]
     L.aw_batch_fetch.argtypes = [vp, vp, RESULT_CB, vp]
@@ -227,6 +232,41 @@ class Context:
         arr = make_pairs(pairs)
         check(lib().aw_align_pairs(self._h, C.byref(params), orientation, arr, len(pairs), flags, cb, None), "aw_align_pairs")
         return out
+
+    def align_stream(self, params, chunks, orientation=AW_ORIENT_MASH, flags=0, callback=None, block_callback=None):
+        """aw_align_stream: `chunks` is an iterable of pair lists (the library pulls one at a time and keeps two in flight);
+        callback(result_dict) and / or block_callback(bytes, n_lines) (needs AW_FLAG_PAF_BLOCKS); non-zero / True cancels"""
+        it = iter(chunks)
+        keep = {}
+        want_bytes = bool(flags & AW_FLAG_CIGAR_BYTES)
+
+        def _next(_u, out):
+            try:
+                ch = next(it)
+            except StopIteration:
+                return 0
+            if not ch:
+                return 0
+            keep["arr"] = make_pairs(ch)  # must stay alive until the following call
+            out[0] = C.cast(keep["arr"], C.POINTER(AwPair))
+            return len(ch)
+
+        def _cb(rp, _u):
+            return int(bool(callback(result_to_dict(rp.contents, want_bytes))))
+
+        def _blk(text, n, lines, _u):
+            return int(bool(block_callback(C.string_at(text, n), lines)))
+
+        src = CHUNK_SOURCE(_next)
+        cb = RESULT_CB(_cb) if callback is not None else C.cast(None, RESULT_CB)
+        blk = PAF_BLOCK_CB(_blk) if block_callback is not None else C.cast(None, PAF_BLOCK_CB)
+        check(lib().aw_align_stream(self._h, C.byref(params), orientation, flags, src, None, cb, blk, None), "aw_align_stream")
+
+    def estimate_divergence(self, pairs):
+        arr = make_pairs(pairs)
+        out = (C.c_float * max(1, len(pairs)))()
+        check(lib().aw_estimate_divergence(self._h, arr, len(pairs), out), "aw_estimate_divergence")
+        return [float(out[i]) for i in range(len(pairs))]
 
     def orient_pairs(self, pairs):
         arr = make_pairs(pairs)

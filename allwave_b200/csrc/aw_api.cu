@@ -67,6 +67,10 @@ struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
     int dev = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }  // early returns park the buffer instead of leaking it
     int ensure(size_t bytes) {
         if (bytes <= cap) return AW_OK;
         release();
@@ -115,6 +119,10 @@ struct DevBuf {
 struct PinBuf {
     void* p = nullptr;
     size_t cap = 0;
+    PinBuf() = default;
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    ~PinBuf() { release(); }
     int ensure(size_t bytes) {
         if (bytes <= cap) return AW_OK;
         release();
@@ -173,6 +181,11 @@ struct aw_ctx {
     int64_t hist_mb = 16;      // base-case history arena per CTA (first attempt)
     int64_t chunk_pairs = 65536;
     int ws16 = 1;              // 1 = int16 wavefront storage when every offset fits
+    int max_retry = 3;         // rungs of the retry ladder (0: a pair whose first-try workspace was too small fails)
+    // streams: `stream` runs the kernels (they serialise: every launch fills the GPU), `up_stream` uploads the next batch's
+    // pair list, `copy_stream` brings the previous batch's results back while the next kernel runs
+    cudaStream_t up_stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_sketch = nullptr;  // recorded after the stranded sketch build; every stream that reads the sketches waits on it
     aw_params orient_params = {0, 1, 1, 1, 0, 0, 0, 0};  // AlignmentParams::edit_distance(), src/iterator.rs:85
     // sequence store
     uint32_t n = 0;
@@ -197,6 +210,7 @@ struct aw_batch {
     uint64_t npairs = 0;
     std::vector<aw_pair> h_pairs;
     DevBuf d_pairs, d_isrev, d_order, d_out, d_text, d_bytes, d_ctl;
+    DevBuf d_text2, d_off;              // AW_FLAG_PAF_BLOCKS: the text arena again in pair order, and the per-pair offsets (n+1)
     DevBuf d_out_f, d_out_r, d_strand;  // --wfa-orientation passes: per-strand results and a constant 0.. / 1.. strand array
     AwPen pen_orient;  // d_ctl: [0] text cursor, [1] bytes cursor, [2] next_pair
     uint64_t text_cap = 0, bytes_cap = 0;
@@ -213,6 +227,7 @@ struct aw_batch {
     uint64_t cyc[6] = {0, 0, 0, 0, 0, 0};
     bool launched = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the alignment kernel of the last launch
+    cudaEvent_t ev_done = nullptr;             // after the last kernel of the launch (what fetch waits for)
 };
 
 struct aw_aligner {
@@ -268,6 +283,9 @@ extern "C" int aw_create(int device, aw_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_sketch, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         aw_set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
         delete c;
@@ -292,6 +310,7 @@ static void free_sketches(aw_ctx* c) {
 extern "C" void aw_destroy(aw_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaDeviceSynchronize();  // nothing of this context may still be running when its buffers are parked for reuse
     free_sketches(c);
     c->d_slots.release();
     c->d_ascii.release();
@@ -304,7 +323,23 @@ extern "C" void aw_destroy(aw_ctx* c) {
     c->ws_seq2.release();
     c->ws_runs.release();
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->up_stream) cudaStreamDestroy(c->up_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_sketch) cudaEventDestroy(c->ev_sketch);
     delete c;
+}
+
+extern "C" void aw_trim_cache(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) n = 0;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (int d = 0; d < n && d < 64; ++d) {
+        cudaSetDevice(d);
+        g_cache.trim_dev(d);
+    }
+    cudaSetDevice(cur);
+    g_cache.trim_pin();
 }
 
 extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
@@ -319,6 +354,7 @@ extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
     else if (k == "chunk_pairs") c->chunk_pairs = value > 0 ? value : 65536;
     else if (k == "band_engine") (void)value;  // accepted for compatibility: the experimental band engine of the first kernels is gone
     else if (k == "ws16") c->ws16 = value ? 1 : 0;
+    else if (k == "max_retry_attempts") c->max_retry = (int)std::max<int64_t>(0, std::min<int64_t>(3, value));
     else return AW_EINVAL;
     return AW_OK;
 }
@@ -339,6 +375,7 @@ extern "C" int aw_set_orientation_params(aw_ctx* c, const aw_params* p) {
 extern "C" int aw_load_sequences(aw_ctx* c, uint32_t n, const uint8_t* const* seqs, const uint64_t* lens, const char* const* ids) {
     if (!c || (n && (!seqs || !lens))) return AW_EINVAL;
     AW_CUDA_CHECK(cudaSetDevice(c->device));
+    AW_CUDA_CHECK(cudaStreamSynchronize(c->stream));  // nothing may still read the store that is about to be replaced
     free_sketches(c);
     c->n = n;
     c->lens.assign(lens, lens + n);
@@ -449,9 +486,14 @@ static int build_sketches(aw_ctx* c, SketchSet& ss, bool canonical, int k, uint3
 }
 
 static int ensure_stranded(aw_ctx* c, cudaStream_t st, uint64_t* launches) {
-    if (c->have_stranded) return AW_OK;
+    if (c->have_stranded) {
+        // the sketches may have been built on another stream: order this one after the build
+        AW_CUDA_CHECK(cudaStreamWaitEvent(st, c->ev_sketch, 0));
+        return AW_OK;
+    }
     int rc = build_sketches(c, c->stranded, false, AW_ORIENT_K, AW_SKETCH_SIZE, st);
     if (rc) return rc;
+    AW_CUDA_CHECK(cudaEventRecord(c->ev_sketch, st));
     c->have_stranded = true;
     if (launches) ++*launches;
     return AW_OK;
@@ -556,6 +598,31 @@ extern "C" int aw_orient_pairs(aw_ctx* c, const aw_pair* pairs, uint64_t npairs,
     return AW_OK;
 }
 
+extern "C" int aw_estimate_divergence(aw_ctx* c, const aw_pair* pairs, uint64_t npairs, float* out) {
+    if (!c || (npairs && (!pairs || !out))) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    for (uint64_t i = 0; i < npairs; ++i)
+        if (pairs[i].query_idx >= c->n || pairs[i].target_idx >= c->n) return AW_EINVAL;
+    if (npairs == 0) return AW_OK;
+    int rc = ensure_stranded(c, c->stream, nullptr);
+    if (rc) return rc;
+    DevBuf dp, dd;
+    if ((rc = dp.ensure(sizeof(aw_pair) * npairs)) || (rc = dd.ensure(4 * npairs))) return rc;
+    cudaError_t e = cudaMemcpyAsync(dp.p, pairs, sizeof(aw_pair) * npairs, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        awk::aw_divergence_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(dp.as<aw_pair>(), npairs, c->stranded.sk.as<uint64_t>(), c->stranded.n.as<uint32_t>(),
+                                                                   c->stranded.size, AW_ORIENT_K, dd.as<float>());
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dd.p, 4 * npairs, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        aw_set_error("aw_estimate_divergence: %s", cudaGetErrorString(e));
+        return AW_ECUDA;
+    }
+    return AW_OK;
+}
+
 // ---- batches -------------------------------------------------------------------------------
 // create_wfa_aligner + AlignmentMode::from_params (src/alignment.rs:263-289, src/types.rs:105-117)
 static int pen_from_params(const aw_params* p, AwPen* pen) {
@@ -592,6 +659,10 @@ static int pen_from_params(const aw_params* p, AwPen* pen) {
 extern "C" void aw_batch_destroy(aw_ctx* c, aw_batch* b) {
     if (!b) return;
     if (c) cudaSetDevice(c->device);
+    if (b->launched) {  // never park buffers a kernel still uses
+        if (b->ev_done) cudaEventSynchronize(b->ev_done);
+        if (c) cudaStreamSynchronize(c->stream);
+    }
     b->d_pairs.release();
     b->d_isrev.release();
     b->d_order.release();
@@ -607,36 +678,27 @@ extern "C" void aw_batch_destroy(aw_ctx* c, aw_batch* b) {
     b->h_bytes.release();
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->ev_done) cudaEventDestroy(b->ev_done);
     delete b;
 }
 
-extern "C" int aw_batch_create(aw_ctx* c, const aw_params* params, int orientation_mode, const aw_pair* pairs, uint64_t npairs, uint32_t flags,
-                               aw_batch** out) {
-    if (!c || !params || !out || (npairs && !pairs)) return AW_EINVAL;
-    *out = nullptr;
-    if (npairs > 0xfffffff0ull) return AW_EINVAL;
-    if (orientation_mode != AW_ORIENT_MASH && orientation_mode != AW_ORIENT_FORWARD && orientation_mode != AW_ORIENT_WFA) return AW_EINVAL;
-    AW_CUDA_CHECK(cudaSetDevice(c->device));
-    aw_batch* b = new aw_batch();
+// (re)initialises a batch object for a new pair list; device / pinned buffers of an earlier use are kept (grow-only)
+static int batch_init(aw_ctx* c, aw_batch* b, const aw_params* params, int orientation_mode, const aw_pair* pairs, uint64_t npairs, uint32_t flags) {
     int rc = pen_from_params(params, &b->pen);
-    if (rc) {
-        delete b;
-        return rc;
-    }
-    if (orientation_mode == AW_ORIENT_WFA && (rc = pen_from_params(&c->orient_params, &b->pen_orient))) {
-        delete b;
-        return rc;
-    }
+    if (rc) return rc;
+    if (orientation_mode == AW_ORIENT_WFA && (rc = pen_from_params(&c->orient_params, &b->pen_orient))) return rc;
     b->orient = orientation_mode;
     b->flags = flags;
     b->npairs = npairs;
+    b->launched = false;
+    b->has_order = false;
+    b->max_p = b->max_t = 0;
     b->h_pairs.assign(pairs, pairs + npairs);
     uint64_t sum_len = 0;
     bool varied = false;
     for (uint64_t i = 0; i < npairs; ++i) {
         if (pairs[i].query_idx >= c->n || pairs[i].target_idx >= c->n) {
             aw_set_error("pair %llu references a sequence index out of range", (unsigned long long)i);
-            delete b;
             return AW_EINVAL;
         }
         const uint64_t pl = c->lens[pairs[i].query_idx], tl = c->lens[pairs[i].target_idx];
@@ -647,41 +709,76 @@ extern "C" int aw_batch_create(aw_ctx* c, const aw_params* params, int orientati
     }
     size_t idlen_max = 0;
     for (auto& s : c->ids) idlen_max = std::max(idlen_max, s.size());
-    b->text_cap = (flags & AW_FLAG_NO_PAF) ? sum_len / 2 + 64 * npairs + 1024 : sum_len + (256 + 2 * idlen_max) * npairs + 1024;
+    b->text_cap = (flags & AW_FLAG_NO_PAF) ? sum_len / 2 + 64 * npairs + 1024 : sum_len + (257 + 2 * idlen_max) * npairs + 1024;
     b->bytes_cap = (flags & AW_FLAG_CIGAR_BYTES) ? sum_len + 16 : 16;
     const size_t np1 = (size_t)std::max<uint64_t>(1, npairs);
     if ((rc = b->d_pairs.ensure(sizeof(aw_pair) * np1)) || (rc = b->d_isrev.ensure(np1)) || (rc = b->d_out.ensure(sizeof(AwPairOut) * np1)) ||
         (rc = b->d_text.ensure(b->text_cap)) || (rc = b->d_bytes.ensure(b->bytes_cap)) || (rc = b->d_ctl.ensure(64)) ||
         (orientation_mode == AW_ORIENT_WFA &&
-         ((rc = b->d_out_f.ensure(sizeof(AwPairOut) * np1)) || (rc = b->d_out_r.ensure(sizeof(AwPairOut) * np1)) || (rc = b->d_strand.ensure(2 * np1))))) {
-        aw_batch_destroy(c, b);
+         ((rc = b->d_out_f.ensure(sizeof(AwPairOut) * np1)) || (rc = b->d_out_r.ensure(sizeof(AwPairOut) * np1)) || (rc = b->d_strand.ensure(2 * np1)))))
         return rc;
-    }
-    cudaError_t e = cudaMemcpyAsync(b->d_pairs.p, pairs, sizeof(aw_pair) * npairs, cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_isrev.p, 0, np1, c->stream);
-    if (e == cudaSuccess && orientation_mode == AW_ORIENT_WFA) e = cudaMemsetAsync(b->d_strand.p, 0, np1, c->stream);
-    if (e == cudaSuccess && orientation_mode == AW_ORIENT_WFA) e = cudaMemsetAsync(b->d_strand.as<uint8_t>() + np1, 1, np1, c->stream);
-    if (e == cudaSuccess && varied) {
-        // heaviest (longest) pairs first: greedy balance of the persistent CTAs
+    if ((flags & AW_FLAG_PAF_BLOCKS) && !(flags & AW_FLAG_NO_PAF) && ((rc = b->d_text2.ensure(b->text_cap)) || (rc = b->d_off.ensure(8 * (np1 + 1))))) return rc;
+    // uploads go through their own stream, so that a batch can be prepared while the previous one is still running
+    cudaStream_t us = c->up_stream;
+    cudaError_t e = cudaMemcpyAsync(b->d_pairs.p, pairs, sizeof(aw_pair) * npairs, cudaMemcpyHostToDevice, us);
+    if (e == cudaSuccess) e = cudaMemsetAsync(b->d_isrev.p, 0, np1, us);
+    if (e == cudaSuccess && orientation_mode == AW_ORIENT_WFA) e = cudaMemsetAsync(b->d_strand.p, 0, np1, us);
+    if (e == cudaSuccess && orientation_mode == AW_ORIENT_WFA) e = cudaMemsetAsync(b->d_strand.as<uint8_t>() + np1, 1, np1, us);
+    // (one-warp kernels for reads up to 1 kb keep the given order: their costs are within a small factor of each other and the
+    // sort + upload would cost more than it saves)
+    if (e == cudaSuccess && varied && std::max(b->max_p, b->max_t) > 1024) {
+        // heaviest pairs first: greedy balance of the persistent CTAs.  Predicted cost = wavefront cells ~ (expected score)^2
+        // with the score estimated from length x divergence (mash distance of the stranded sketches) + length difference
         std::vector<uint32_t> order(npairs);
-        for (uint64_t i = 0; i < npairs; ++i) order[i] = (uint32_t)i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t bb) {
-            const uint64_t la = c->lens[pairs[a].query_idx] + c->lens[pairs[a].target_idx];
-            const uint64_t lb = c->lens[pairs[bb].query_idx] + c->lens[pairs[bb].target_idx];
-            return la > lb;
-        });
-        if ((rc = b->d_order.ensure(4 * np1))) {
-            aw_batch_destroy(c, b);
-            return rc;
+        std::vector<double> cost(npairs);
+        std::vector<float> div;
+        if (orientation_mode == AW_ORIENT_MASH) {  // the sketches are (or will be) there anyway: estimate every pair's divergence
+            DevBuf dd;
+            if ((rc = ensure_stranded(c, us, nullptr)) || (rc = dd.ensure(4 * np1))) return rc;
+            div.resize(npairs);
+            awk::aw_divergence_kernel<<<c->sm_count * 8, 256, 0, us>>>(b->d_pairs.as<aw_pair>(), npairs, c->stranded.sk.as<uint64_t>(),
+                                                                c->stranded.n.as<uint32_t>(), c->stranded.size, AW_ORIENT_K, dd.as<float>());
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(div.data(), dd.p, 4 * (size_t)npairs, cudaMemcpyDeviceToHost, us);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(us);
+            if (e != cudaSuccess) {
+                aw_set_error("aw_batch_create: %s", cudaGetErrorString(e));
+                return AW_ECUDA;
+            }
         }
-        e = cudaMemcpy(b->d_order.p, order.data(), 4 * (size_t)npairs, cudaMemcpyHostToDevice);
+        for (uint64_t i = 0; i < npairs; ++i) {
+            order[i] = (uint32_t)i;
+            const double pl = (double)c->lens[pairs[i].query_idx], tl = (double)c->lens[pairs[i].target_idx];
+            const double d = div.empty() ? 0.05 : std::min(0.5, std::max(1e-3, (double)div[i]));
+            const double sc = std::max(pl, tl) * d + std::fabs(pl - tl);
+            cost[i] = sc * sc + pl + tl;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t bb) { return cost[a] > cost[bb]; });
+        if ((rc = b->d_order.ensure(4 * np1))) return rc;
+        e = cudaMemcpyAsync(b->d_order.p, order.data(), 4 * (size_t)npairs, cudaMemcpyHostToDevice, us);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(us);  // `order` dies with this scope
         b->has_order = true;
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(us);
     if (e != cudaSuccess) {
         aw_set_error("aw_batch_create: %s", cudaGetErrorString(e));
-        aw_batch_destroy(c, b);
         return AW_ECUDA;
+    }
+    return AW_OK;
+}
+
+extern "C" int aw_batch_create(aw_ctx* c, const aw_params* params, int orientation_mode, const aw_pair* pairs, uint64_t npairs, uint32_t flags,
+                               aw_batch** out) {
+    if (!c || !params || !out || (npairs && !pairs)) return AW_EINVAL;
+    *out = nullptr;
+    if (npairs > 0xfffffff0ull) return AW_EINVAL;
+    if (orientation_mode != AW_ORIENT_MASH && orientation_mode != AW_ORIENT_FORWARD && orientation_mode != AW_ORIENT_WFA) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    aw_batch* b = new aw_batch();
+    int rc = batch_init(c, b, params, orientation_mode, pairs, npairs, flags);
+    if (rc) {
+        aw_batch_destroy(c, b);
+        return rc;
     }
     *out = b;
     return AW_OK;
@@ -827,6 +924,11 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     // pairs too long for the shared-memory staging keep their 4 word-pair arrays (pattern, text, both reversed) per CTA
     cfg->seq2_cap = (!ws16 && nt >= 64 && c->all_clean) ? 2 * ((max_p / 16 + 2) + (max_t / 16 + 2)) : 0;
     int rc;
+    // growing a workspace re-allocates it: a kernel of an earlier batch that is still running must not lose its buffers
+    if (grid * ws_ints * 4 > c->ws_main.cap || grid * 2ull * (pen.scope + 1) * (uint64_t)cfg->blk_cap * 2 * 4 > c->ws_blk.cap ||
+        grid * cfg->seq2_cap * 8 + 16 > c->ws_seq2.cap || grid * (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 > c->ws_hist_meta.cap ||
+        grid * runs_cap * 8 > c->ws_runs.cap)
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return AW_ECUDA;
     if ((rc = c->ws_main.ensure(grid * ws_ints * 4)) ||
         (rc = c->ws_blk.ensure(grid * 2ull * (pen.scope + 1) * (uint64_t)cfg->blk_cap * 2 * 4)) ||
         (rc = c->ws_seq2.ensure(grid * cfg->seq2_cap * 8 + 16)) ||
@@ -932,6 +1034,7 @@ extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
     if (!b->ev0) {
         AW_CUDA_CHECK(cudaEventCreate(&b->ev0));
         AW_CUDA_CHECK(cudaEventCreate(&b->ev1));
+        AW_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
     }
     AW_CUDA_CHECK(cudaEventRecord(b->ev0, st));
     cudaError_t e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.ws16, cfg.grid, st);
@@ -940,7 +1043,94 @@ extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
         return AW_ECUDA;
     }
     AW_CUDA_CHECK(cudaEventRecord(b->ev1, st));
+    if ((b->flags & AW_FLAG_PAF_BLOCKS) && !(b->flags & AW_FLAG_NO_PAF)) {
+        awk::aw_text_scan_kernel<<<1, 1024, 0, st>>>(b->d_out.as<AwPairOut>(), (uint32_t)b->npairs, b->d_off.as<unsigned long long>());
+        awk::aw_text_gather_kernel<<<c->sm_count * 8, 256, 0, st>>>(b->d_out.as<AwPairOut>(), b->d_off.as<unsigned long long>(), (uint32_t)b->npairs,
+                                                                  b->d_text.as<char>(), b->d_text2.as<char>());
+        AW_CUDA_CHECK(cudaGetLastError());
+        b->stats[0] += 2;
+    }
+    AW_CUDA_CHECK(cudaEventRecord(b->ev_done, st));
     ++b->stats[0];
+    return AW_OK;
+}
+
+// --wfa-orientation, pairs whose first-try orientation passes ran out of workspace (strand 2 = undecided): both count-only
+// passes go through the same ladder as the alignment itself, then the strand is picked like determine_orientation_wfa
+// (src/alignment.rs:157-175: a pass that still fails after the ladder counts as usize::MAX)
+static int retry_orientation(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
+    std::vector<uint32_t> todo;
+    for (uint64_t i = 0; i < b->npairs; ++i)
+        if (h_out[i].status == AW_EWORKSPACE && h_out[i].is_reverse > 1) todo.push_back((uint32_t)i);
+    if (todo.empty()) return AW_OK;
+    const size_t np1 = (size_t)std::max<uint64_t>(1, b->npairs);
+    std::vector<AwPairOut> of(b->npairs), orv(b->npairs);
+    std::vector<uint8_t> strand(b->npairs, 0);
+    std::vector<uint8_t> have_f(b->npairs, 0), have_r(b->npairs, 0);
+    std::vector<unsigned long long> ed_f(b->npairs, ~0ull), ed_r(b->npairs, ~0ull);
+    for (int attempt = 1; attempt <= std::max(1, c->max_retry) && !todo.empty(); ++attempt) {
+        uint64_t max_p = 0, max_t = 0;
+        for (uint32_t i : todo) {
+            max_p = std::max(max_p, c->lens[b->h_pairs[i].query_idx]);
+            max_t = std::max(max_t, c->lens[b->h_pairs[i].target_idx]);
+        }
+        LaunchCfg cfo;
+        int rc = plan_launch(c, b->pen_orient, todo.size(), max_p, max_t, attempt, &cfo);
+        if (rc) return rc;
+        DevBuf d_order, d_ctl;
+        if ((rc = d_order.ensure(4 * todo.size())) || (rc = d_ctl.ensure(64))) return rc;
+        cudaError_t e = cudaMemcpy(d_order.p, todo.data(), 4 * todo.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemset(d_ctl.p, 0, 64);
+        for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
+            awk::KParams Q;
+            fill_params(c, b, b->pen_orient, cfo, &Q);
+            Q.flags = AW_KFLAG_COUNT_ONLY | AW_FLAG_NO_PAF;
+            Q.is_reverse = b->d_strand.as<uint8_t>() + s * np1;
+            Q.order = d_order.as<uint32_t>();
+            Q.npairs = (uint32_t)todo.size();
+            Q.next_pair = reinterpret_cast<unsigned int*>(d_ctl.as<unsigned long long>() + 3 + s);
+            Q.out = (s == 0 ? b->d_out_f : b->d_out_r).as<AwPairOut>();
+            Q.text = b->d_text.as<char>();
+            Q.text_cursor = d_ctl.as<unsigned long long>() + 5;
+            Q.text_cap = b->text_cap;
+            Q.bytes = b->d_bytes.as<uint8_t>();
+            Q.bytes_cursor = d_ctl.as<unsigned long long>() + 6;
+            Q.bytes_cap = b->bytes_cap;
+            e = dispatch_align(Q, cfo.nt, c->all_clean ? 2 : 8, b->pen_orient.two_piece != 0, cfo.ws16, cfo.grid, c->stream);
+            ++b->stats[0];
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = cudaMemcpy(of.data(), b->d_out_f.p, sizeof(AwPairOut) * b->npairs, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(orv.data(), b->d_out_r.p, sizeof(AwPairOut) * b->npairs, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            aw_set_error("orientation retry: %s", cudaGetErrorString(e));
+            return AW_ECUDA;
+        }
+        std::vector<uint32_t> still;
+        const bool last = attempt >= std::max(1, c->max_retry);
+        for (uint32_t i : todo) {
+            if (!have_f[i] && (of[i].status != AW_EWORKSPACE || last)) {
+                have_f[i] = 1;
+                ed_f[i] = of[i].status == AW_OK ? of[i].n_x + of[i].n_i + of[i].n_d : ~0ull;
+            }
+            if (!have_r[i] && (orv[i].status != AW_EWORKSPACE || last)) {
+                have_r[i] = 1;
+                ed_r[i] = orv[i].status == AW_OK ? orv[i].n_x + orv[i].n_i + orv[i].n_d : ~0ull;
+            }
+            if (have_f[i] && have_r[i]) strand[i] = ed_f[i] <= ed_r[i] ? 0 : 1;
+            else still.push_back(i);
+        }
+        todo.swap(still);
+    }
+    // publish the decided strands (everything else in d_isrev is untouched)
+    for (uint64_t i = 0; i < b->npairs; ++i)
+        if (h_out[i].status == AW_EWORKSPACE && h_out[i].is_reverse > 1) {
+            cudaError_t e = cudaMemcpy(b->d_isrev.as<uint8_t>() + i, &strand[i], 1, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) {
+                aw_set_error("orientation retry: %s", cudaGetErrorString(e));
+                return AW_ECUDA;
+            }
+        }
     return AW_OK;
 }
 
@@ -951,7 +1141,26 @@ static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
         if (h_out[i].status == AW_EWORKSPACE) failed.push_back((uint32_t)i);
     if (failed.empty()) return AW_OK;
     b->stats[1] = failed.size();
+    // a later batch of the same context may already be running with the current workspace: let it finish before the
+    // workspace is re-planned (and possibly re-allocated) for the retry
+    AW_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (b->orient == AW_ORIENT_WFA) {
+        int rc = retry_orientation(c, b, h_out);
+        if (rc) return rc;
+    }
+    const unsigned nl = (b->flags & AW_FLAG_PAF_BLOCKS) ? 1u : 0u;
     for (int attempt = 1; attempt <= 3 && !failed.empty(); ++attempt) {
+        const bool give_up = attempt > c->max_retry;  // ladder disabled or exhausted: report the pairs as failed
+        if (give_up) {
+            for (uint32_t i : failed) {
+                AwPairOut o = h_out[i];
+                o.status = AW_EALIGN;
+                b->r_idx.push_back(i);
+                b->r_out.push_back(o);
+            }
+            failed.clear();
+            break;
+        }
         uint64_t max_p = 0, max_t = 0, sum_len = 0;
         size_t idlen_max = 0;
         for (uint32_t i : failed) {
@@ -995,11 +1204,6 @@ static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
         std::vector<uint8_t> bytes(std::min<uint64_t>(ctl[1], bytes_cap));
         if (e == cudaSuccess && !text.empty()) e = cudaMemcpy(text.data(), d_text.p, text.size(), cudaMemcpyDeviceToHost);
         if (e == cudaSuccess && !bytes.empty()) e = cudaMemcpy(bytes.data(), d_bytes.p, bytes.size(), cudaMemcpyDeviceToHost);
-        d_order.release();
-        d_out.release();
-        d_text.release();
-        d_bytes.release();
-        d_ctl.release();
         if (e != cudaSuccess) {
             aw_set_error("retry launch: %s", cudaGetErrorString(e));
             return AW_ECUDA;
@@ -1013,7 +1217,7 @@ static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
             }
             if (o.status == AW_OK) {
                 const uint64_t toff = b->r_text.size(), boff = b->r_bytes.size();
-                b->r_text.insert(b->r_text.end(), text.begin() + o.paf_off, text.begin() + o.paf_off + o.paf_len);
+                b->r_text.insert(b->r_text.end(), text.begin() + o.paf_off, text.begin() + o.paf_off + o.paf_len + (o.paf_len ? nl : 0));
                 const uint64_t nb = (b->flags & AW_FLAG_CIGAR_BYTES) ? o.n_m + o.n_x + o.n_i + o.n_d : 0;
                 if (nb) b->r_bytes.insert(b->r_bytes.end(), bytes.begin() + o.bytes_off, bytes.begin() + o.bytes_off + nb);
                 o.paf_off = toff;
@@ -1027,41 +1231,69 @@ static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
     return AW_OK;
 }
 
-extern "C" int aw_batch_fetch(aw_ctx* c, aw_batch* b, aw_result_cb cb, void* user) {
-    if (!c || !b || !b->launched) return AW_EINVAL;
-    AW_CUDA_CHECK(cudaSetDevice(c->device));
+// joins the batch's launch (an event, not a device-wide sync: another batch of the same context may be running), copies the
+// results back on the context's copy stream and delivers them
+static int fetch_impl(aw_ctx* c, aw_batch* b, aw_result_cb cb, aw_paf_block_cb block_cb, void* user) {
     if (b->npairs == 0) return AW_OK;
-    // the launch may sit on a caller stream: a device-wide sync is the only portable join
-    AW_CUDA_CHECK(cudaDeviceSynchronize());
+    AW_CUDA_CHECK(cudaEventSynchronize(b->ev_done));
+    cudaStream_t cs = c->copy_stream;
     int rc;
     unsigned long long ctl[3] = {0, 0, 0};
-    AW_CUDA_CHECK(cudaMemcpy(ctl, b->d_ctl.p, 24, cudaMemcpyDeviceToHost));
+    if ((rc = b->h_out.ensure(sizeof(AwPairOut) * b->npairs + 64))) return rc;
+    unsigned long long* h_ctl = reinterpret_cast<unsigned long long*>(b->h_out.as<char>() + sizeof(AwPairOut) * b->npairs);  // pinned
+    AW_CUDA_CHECK(cudaMemcpyAsync(h_ctl, b->d_ctl.p, 24, cudaMemcpyDeviceToHost, cs));
+    AW_CUDA_CHECK(cudaMemcpyAsync(b->h_out.p, b->d_out.p, sizeof(AwPairOut) * b->npairs, cudaMemcpyDeviceToHost, cs));
+    AW_CUDA_CHECK(cudaStreamSynchronize(cs));
+    memcpy(ctl, h_ctl, 24);
     const uint64_t text_used = std::min<uint64_t>(ctl[0], b->text_cap), bytes_used = std::min<uint64_t>(ctl[1], b->bytes_cap);
-    if ((rc = b->h_out.ensure(sizeof(AwPairOut) * b->npairs)) || (rc = b->h_text.ensure(text_used + 1)) || (rc = b->h_bytes.ensure(bytes_used + 1))) return rc;
-    AW_CUDA_CHECK(cudaMemcpyAsync(b->h_out.p, b->d_out.p, sizeof(AwPairOut) * b->npairs, cudaMemcpyDeviceToHost, c->stream));
-    if (text_used) AW_CUDA_CHECK(cudaMemcpyAsync(b->h_text.p, b->d_text.p, text_used, cudaMemcpyDeviceToHost, c->stream));
-    if (bytes_used && (b->flags & AW_FLAG_CIGAR_BYTES)) AW_CUDA_CHECK(cudaMemcpyAsync(b->h_bytes.p, b->d_bytes.p, bytes_used, cudaMemcpyDeviceToHost, c->stream));
-    AW_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if ((rc = b->h_text.ensure(text_used + 1)) || (rc = b->h_bytes.ensure(bytes_used + 1))) return rc;
+    // block mode: the arena was re-laid out in pair order on the device (every line followed by '\n')
+    const bool ordered = (b->flags & AW_FLAG_PAF_BLOCKS) && !(b->flags & AW_FLAG_NO_PAF);
+    if (text_used) AW_CUDA_CHECK(cudaMemcpyAsync(b->h_text.p, ordered ? b->d_text2.p : b->d_text.p, text_used, cudaMemcpyDeviceToHost, cs));
+    if (bytes_used && (b->flags & AW_FLAG_CIGAR_BYTES)) AW_CUDA_CHECK(cudaMemcpyAsync(b->h_bytes.p, b->d_bytes.p, bytes_used, cudaMemcpyDeviceToHost, cs));
+    AW_CUDA_CHECK(cudaStreamSynchronize(cs));
     const AwPairOut* outs = b->h_out.as<AwPairOut>();
     if ((rc = retry_failed(c, b, outs))) return rc;
     std::vector<int64_t> retry_of(b->r_idx.empty() ? 0 : b->npairs, -1);
     for (size_t j = 0; j < b->r_idx.size(); ++j) retry_of[b->r_idx[j]] = (int64_t)j;
     b->stats[2] = text_used + b->r_text.size();
+    const bool blocks = block_cb && (b->flags & AW_FLAG_PAF_BLOCKS) && !(b->flags & AW_FLAG_NO_PAF);
+    const unsigned nl = (b->flags & AW_FLAG_PAF_BLOCKS) ? 1u : 0u;
+    const bool all_first_try = b->r_idx.empty();
+    // the whole arena is one gap-free block of newline-terminated lines when every pair succeeded at the first try
+    if (blocks && all_first_try && text_used && block_cb(b->h_text.as<char>(), text_used, b->npairs, user) != 0) return AW_ECALLBACK;
     std::string sentinel;
+    if (blocks && all_first_try && !cb) {  // nothing per pair is wanted: only the counters
+        for (uint64_t i = 0; i < b->npairs; ++i) {
+            const AwPairOut* o = &outs[i];
+            b->stats[3] += o->nruns;
+            b->stats[4] += std::max(o->n_m + o->n_x + o->n_d, o->n_m + o->n_x + o->n_i);
+            b->stats[6] += o->cells;
+            b->stats[7] += o->steps;
+        }
+        return AW_OK;
+    }
+    uint64_t ordered_off = 0;  // running offset of pair i's line in the ordered arena
     for (uint64_t i = 0; i < b->npairs; ++i) {
         const AwPairOut* o = &outs[i];
         const char* text = b->h_text.as<char>();
         const uint8_t* bytes = b->h_bytes.as<uint8_t>();
+        uint64_t paf_off = o->paf_off;
+        if (ordered) {
+            paf_off = ordered_off;
+            if (o->status == AW_OK && o->paf_len) ordered_off += o->paf_len + 1ull;
+        }
         if (!retry_of.empty() && retry_of[i] >= 0) {
             o = &b->r_out[retry_of[i]];
             text = b->r_text.data();
             bytes = b->r_bytes.data();
+            paf_off = o->paf_off;
         }
         aw_result r;
         memset(&r, 0, sizeof(r));
         r.query_idx = b->h_pairs[i].query_idx;
         r.target_idx = b->h_pairs[i].target_idx;
-        r.is_reverse = (uint8_t)o->is_reverse;
+        r.is_reverse = (uint8_t)(o->is_reverse == 1);
         if (o->status == AW_OK) {
             r.status = AW_OK;
             r.score = o->score;
@@ -1069,9 +1301,9 @@ extern "C" int aw_batch_fetch(aw_ctx* c, aw_batch* b, aw_result_cb cb, void* use
             r.target_end = o->n_m + o->n_x + o->n_i;
             r.num_matches = o->n_m;
             r.alignment_length = o->n_m + o->n_x;
-            r.paf = (b->flags & AW_FLAG_NO_PAF) ? nullptr : text + o->paf_off;
+            r.paf = (b->flags & AW_FLAG_NO_PAF) ? nullptr : text + paf_off;
             r.paf_len = (b->flags & AW_FLAG_NO_PAF) ? 0 : o->paf_len;
-            r.cg = text + o->paf_off + o->cg_off;
+            r.cg = text + paf_off + o->cg_off;
             r.cg_len = o->paf_len - o->cg_off;
             if (b->flags & AW_FLAG_CIGAR_BYTES) {
                 r.cigar_bytes = bytes + o->bytes_off;
@@ -1082,6 +1314,7 @@ extern "C" int aw_batch_fetch(aw_ctx* c, aw_batch* b, aw_result_cb cb, void* use
             b->stats[6] += o->cells;
             b->stats[7] += o->steps;
             for (int q = 0; q < 6; ++q) b->cyc[q] += o->cyc[q];
+            if (blocks && !all_first_try && block_cb(r.paf, r.paf_len + nl, 1, user) != 0) return AW_ECALLBACK;
         } else {
             // the reference's failure sentinel (src/alignment.rs:49-64) still becomes a PAF line
             r.status = AW_EALIGN;
@@ -1095,14 +1328,22 @@ extern "C" int aw_batch_fetch(aw_ctx* c, aw_batch* b, aw_result_cb cb, void* use
                 sentinel += c->ids[r.target_idx];
                 snprintf(buf, sizeof(buf), "\t%llu\t0\t0\t0\t0\t60\tgi:f:0.000000\tcg:Z:", (unsigned long long)c->lens[r.target_idx]);
                 sentinel += buf;
+                if (nl) sentinel += '\n';
                 r.paf = sentinel.data();
-                r.paf_len = sentinel.size();
+                r.paf_len = sentinel.size() - nl;
                 r.cg = r.paf + r.paf_len;
+                if (blocks && block_cb(r.paf, r.paf_len + nl, 1, user) != 0) return AW_ECALLBACK;
             }
         }
         if (cb && cb(&r, user) != 0) return AW_ECALLBACK;
     }
     return AW_OK;
+}
+
+extern "C" int aw_batch_fetch(aw_ctx* c, aw_batch* b, aw_result_cb cb, void* user) {
+    if (!c || !b || !b->launched) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    return fetch_impl(c, b, cb, nullptr, user);
 }
 
 extern "C" int aw_batch_kernel_ms(aw_ctx* c, aw_batch* b, float* out_ms) {
@@ -1125,22 +1366,62 @@ extern "C" int aw_batch_stats(aw_ctx* c, aw_batch* b, uint64_t out[8]) {
     return AW_OK;
 }
 
+// The streaming driver: two batch objects alternate.  While batch k's kernel runs on c->stream, batch k+1's pair list is
+// uploaded (up_stream) and its kernels are queued behind it; batch k is then joined by its event, copied back on copy_stream
+// and delivered while batch k+1 computes.  Nothing here synchronises the device.
+extern "C" int aw_align_stream(aw_ctx* c, const aw_params* params, int orientation_mode, uint32_t flags, aw_chunk_source next, void* next_user,
+                               aw_result_cb cb, aw_paf_block_cb block_cb, void* user) {
+    if (!c || !params || !next) return AW_EINVAL;
+    if (orientation_mode != AW_ORIENT_MASH && orientation_mode != AW_ORIENT_FORWARD && orientation_mode != AW_ORIENT_WFA) return AW_EINVAL;
+    AW_CUDA_CHECK(cudaSetDevice(c->device));
+    aw_batch* slot[2] = {new aw_batch(), new aw_batch()};
+    bool busy[2] = {false, false};
+    int rc = AW_OK;
+    auto feed = [&](int s) -> int {  // pulls the next chunk into slot s and queues its kernels; busy[s] says whether there was one
+        const aw_pair* pairs = nullptr;
+        const uint64_t n = next(next_user, &pairs);
+        if (n == 0) return AW_OK;
+        if (!pairs || n > 0xfffffff0ull) return AW_EINVAL;
+        int r = batch_init(c, slot[s], params, orientation_mode, pairs, n, flags);
+        if (r == AW_OK) r = aw_batch_launch(c, slot[s], nullptr);
+        busy[s] = (r == AW_OK);
+        return r;
+    };
+    rc = feed(0);
+    for (int k = 0; rc == AW_OK && busy[k & 1]; ++k) {
+        rc = feed((k + 1) & 1);
+        if (rc != AW_OK) break;
+        rc = fetch_impl(c, slot[k & 1], cb, block_cb, user);
+        busy[k & 1] = false;
+    }
+    for (int s = 0; s < 2; ++s) aw_batch_destroy(c, slot[s]);  // waits for a batch that is still in flight (cancelled run)
+    return rc;
+}
+
+namespace {
+struct ArraySource {
+    const aw_pair* pairs;
+    uint64_t n, pos, chunk;
+    static uint64_t next(void* user, const aw_pair** out) {
+        ArraySource* a = static_cast<ArraySource*>(user);
+        if (a->pos >= a->n) return 0;
+        const uint64_t cnt = std::min<uint64_t>(a->chunk, a->n - a->pos);
+        *out = a->pairs + a->pos;
+        a->pos += cnt;
+        return cnt;
+    }
+};
+}  // namespace
+
 extern "C" int aw_align_pairs(aw_ctx* c, const aw_params* params, int orientation_mode, const aw_pair* pairs, uint64_t npairs, uint32_t flags,
                               aw_result_cb cb, void* user) {
     if (!c || !params || (npairs && !pairs)) return AW_EINVAL;
-    const uint64_t chunk = (uint64_t)c->chunk_pairs;
-    for (uint64_t off = 0; off < npairs || (npairs == 0 && off == 0); off += chunk) {
-        const uint64_t cnt = std::min<uint64_t>(chunk, npairs - off);
-        aw_batch* b = nullptr;
-        int rc = aw_batch_create(c, params, orientation_mode, pairs + off, cnt, flags, &b);
-        if (rc) return rc;
-        rc = aw_batch_launch(c, b, nullptr);
-        if (rc == AW_OK) rc = aw_batch_fetch(c, b, cb, user);
-        aw_batch_destroy(c, b);
-        if (rc) return rc;
-        if (npairs == 0) break;
+    if (npairs == 0) {  // still validates the parameters like a real call
+        AwPen pen;
+        return pen_from_params(params, &pen);
     }
-    return AW_OK;
+    ArraySource src{pairs, npairs, 0, (uint64_t)c->chunk_pairs};
+    return aw_align_stream(c, params, orientation_mode, flags & ~AW_FLAG_PAF_BLOCKS, &ArraySource::next, &src, cb, nullptr, user);
 }
 
 // ---- lib_wfa2::AffineWavefronts-shaped API -------------------------------------------------

@@ -273,13 +273,77 @@ __global__ void aw_orient_kernel(const aw_pair* __restrict__ pairs, uint64_t npa
     }
 }
 
+// Per-pair divergence estimate for cost-ordered scheduling (BASELINE north_star: "greedy partitioner balanced by predicted
+// cost (length times divergence)"): mash distance -1/k ln(2j/(1+j)) of the better of the two stranded Jaccards, i.e. of the
+// strand determine_orientation_mash will pick.  Scheduling only: never enters a result.
+__global__ void aw_divergence_kernel(const aw_pair* __restrict__ pairs, uint64_t npairs, const uint64_t* __restrict__ sk, const uint32_t* __restrict__ sk_n,
+                                     uint32_t sketch_size, int k, float* __restrict__ out) {
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t p = warp; p < npairs; p += nwarps) {
+        const uint32_t q = pairs[p].query_idx, t = pairs[p].target_idx;
+        const uint64_t* T = sk + (size_t)(2 * t) * sketch_size;
+        uint32_t fi, fu, ri, ru;
+        warp_jaccard_counts(sk + (size_t)(2 * q) * sketch_size, sk_n[2 * q], T, sk_n[2 * t], fi, fu);
+        warp_jaccard_counts(sk + (size_t)(2 * q + 1) * sketch_size, sk_n[2 * q + 1], T, sk_n[2 * t], ri, ru);
+        const double fj = fu == 0 ? 0.0 : (double)fi / (double)fu, rj = ru == 0 ? 0.0 : (double)ri / (double)ru;
+        const double j = fj >= rj ? fj : rj;
+        double d = 1.0;
+        if (j > 0.0) d = -log(2.0 * j / (1.0 + j)) / (double)k;
+        if ((threadIdx.x & 31) == 0) out[p] = (float)fmin(fmax(d, 0.0), 1.0);
+    }
+}
+
 // determine_orientation_wfa (src/alignment.rs:157-175): compare the X+I+D column counts of the two
 // orientation alignments; fwd <= rev keeps the forward strand; a failed alignment counts as usize::MAX
 __global__ void aw_wfa_orient_pick_kernel(const AwPairOut* __restrict__ fwd, const AwPairOut* __restrict__ rev, uint64_t npairs, uint8_t* __restrict__ is_reverse) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < npairs; i += (uint64_t)gridDim.x * blockDim.x) {
         const unsigned long long f = fwd[i].status == AW_OK ? fwd[i].n_x + fwd[i].n_i + fwd[i].n_d : ~0ull;
         const unsigned long long r = rev[i].status == AW_OK ? rev[i].n_x + rev[i].n_i + rev[i].n_d : ~0ull;
-        is_reverse[i] = (f <= r) ? 0 : 1;
+        // a pass that ran out of first-try workspace has not failed: the strand stays undecided (2) and the host re-runs
+        // both passes through the retry ladder before the pair is aligned (the reference completes both alignments)
+        const bool undecided = fwd[i].status == AW_EWORKSPACE || rev[i].status == AW_EWORKSPACE;
+        is_reverse[i] = undecided ? 2 : ((f <= r) ? 0 : 1);
+    }
+}
+
+// ---- ordered PAF text (AW_FLAG_PAF_BLOCKS): the alignment kernel appends lines to the text arena in completion order; these
+// two kernels lay them out again in PAIR order (the order the reference's writer sees with one worker thread,
+// src/main.rs:347-374), so a whole batch leaves the GPU as one ready-to-write block of newline-terminated lines.
+// off[i] = byte offset of pair i's line in the ordered arena, off[n] = total; one block, exclusive scan of (paf_len + 1)
+__global__ void aw_text_scan_kernel(const AwPairOut* __restrict__ out, uint32_t n, unsigned long long* __restrict__ off) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = min(n, threadIdx.x * per), e = min(n, b + per);
+    unsigned long long sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += (out[i].status == AW_OK && out[i].paf_len) ? out[i].paf_len + 1ull : 0ull;
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (unsigned d = 1; d < blockDim.x; d <<= 1) {
+        const unsigned long long t = threadIdx.x >= d ? part[threadIdx.x - d] : 0ull;
+        __syncthreads();
+        part[threadIdx.x] += t;
+        __syncthreads();
+    }
+    unsigned long long run = part[threadIdx.x] - sum;
+    for (uint32_t i = b; i < e; ++i) {
+        off[i] = run;
+        run += (out[i].status == AW_OK && out[i].paf_len) ? out[i].paf_len + 1ull : 0ull;
+    }
+    if (threadIdx.x == blockDim.x - 1) off[n] = part[threadIdx.x];
+}
+// one warp per pair: copy line + '\n' from the completion-order arena to its slot of the ordered arena
+__global__ void aw_text_gather_kernel(const AwPairOut* __restrict__ out, const unsigned long long* __restrict__ off, uint32_t n, const char* __restrict__ src,
+                                      char* __restrict__ dst) {
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    const unsigned lane = threadIdx.x & 31;
+    for (uint64_t p = warp; p < n; p += nwarps) {
+        if (out[p].status != AW_OK || out[p].paf_len == 0) continue;
+        const char* s = src + out[p].paf_off;
+        char* d = dst + off[p];
+        const unsigned len = out[p].paf_len + 1;
+        for (unsigned i = lane; i < len; i += 32) d[i] = s[i];
     }
 }
 

@@ -1033,6 +1033,19 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         const unsigned pair_i = P.order ? P.order[work_i] : work_i;
         const aw_pair pr = P.pairs[pair_i];
         const unsigned is_rev = P.is_reverse ? P.is_reverse[pair_i] : 0u;
+        if (is_rev > 1u) {
+            // --wfa-orientation: one of the two orientation alignments ran out of workspace, the strand is undecided.
+            // Nothing is aligned here; the host decides the strand with a larger workspace and re-runs the pair.
+            if (tid == 0) {
+                AwPairOut o;
+                memset(&o, 0, sizeof(o));
+                o.status = AW_EWORKSPACE;
+                o.score = INT_MAX;
+                o.is_reverse = is_rev;
+                P.out[pair_i] = o;
+            }
+            continue;
+        }
         const AwSlot qs = P.slots[2 * pr.query_idx + is_rev];
         const AwSlot ts = P.slots[2 * pr.target_idx];
         const uint32_t* pw = (BITS == 2) ? P.packed + qs.packed_off : reinterpret_cast<const uint32_t*>(P.ascii + qs.ascii_off);
@@ -2227,18 +2240,21 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         // header: q qlen qs qe strand t tlen ts te matches block 60 gi:f:x.xxxxxx cg:Z:
         const unsigned hdr_len = (qid1 - qid0) + 1 + ndigits(PLEN) + 1 + 1 + 1 + ndigits(q_end) + 1 + 1 + 1 + (tid1 - tid0) + 1 + ndigits(TLEN) + 1 + 1 + 1 +
                                  ndigits(t_end) + 1 + ndigits(n_m) + 1 + ndigits(block_len) + 1 + 2 + 1 + 5 + 8 + 1 + 5;
-        const unsigned long long line_len = count_only ? 0 : (want_paf ? hdr_len + cg_len : cg_len);
-        const unsigned long long nbytes = (!count_only && (P.flags & AW_FLAG_CIGAR_BYTES)) ? (n_m + n_x + n_i + n_d) : 0;
+        // a failed pair reserves nothing, so the text arena stays gap-free (AW_FLAG_PAF_BLOCKS hands it out as one block)
+        const unsigned long long line_len = (count_only || status != ST_OK) ? 0 : (want_paf ? hdr_len + cg_len : cg_len);
+        const unsigned long long nl = (line_len && (P.flags & AW_FLAG_PAF_BLOCKS)) ? 1 : 0;  // '\n' after the line, not counted in paf_len
+        const unsigned long long nbytes = (status == ST_OK && !count_only && (P.flags & AW_FLAG_CIGAR_BYTES)) ? (n_m + n_x + n_i + n_d) : 0;
         if (tid == 0) {
-            s_text_off = atomicAdd(P.text_cursor, line_len);
+            s_text_off = atomicAdd(P.text_cursor, line_len + nl);
             s_bytes_off = nbytes ? atomicAdd(P.bytes_cursor, nbytes) : 0ull;
         }
         cta_sync<NT>();
         const unsigned long long text_off = s_text_off, bytes_off = s_bytes_off;
-        if (status == ST_OK && (text_off + line_len > P.text_cap || bytes_off + nbytes > P.bytes_cap)) status = ST_FAIL_WORKSPACE;
+        if (status == ST_OK && (text_off + line_len + nl > P.text_cap || bytes_off + nbytes > P.bytes_cap)) status = ST_FAIL_WORKSPACE;
         if (status == ST_OK && !count_only) {
             char* line = P.text + text_off;
             char* cg = line;
+            if (nl && tid == 32 % NT) line[line_len] = '\n';
             if (want_paf) {
                 cg = line + hdr_len;
                 if (tid == 0) {

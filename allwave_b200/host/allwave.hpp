@@ -15,6 +15,10 @@
 // partitions them and forwards results.
 #pragma once
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -51,7 +55,8 @@ struct AlignmentParams {
     std::optional<int32_t> gap2_open = 24;
     std::optional<int32_t> gap2_extend = 1;
     std::optional<double> max_divergence;
-    static AlignmentParams edit_distance() {
+    // (noinline: g++ 13.3 crashes in its GIMPLE ccp pass when this is folded into a constructor's member initialiser)
+    __attribute__((noinline)) static AlignmentParams edit_distance() {
         AlignmentParams p;
         p.mismatch_penalty = p.gap_open = p.gap_extend = 1;
         p.gap2_open.reset();
@@ -372,15 +377,18 @@ inline std::vector<std::pair<size_t, size_t>> build_pair_list(Context& ctx, cons
 using Callback = std::function<void(const AlignmentResult&)>;  // throw to abort the run (mirrors a callback Err)
 
 // ---- multi-GPU sharding: the path shards by independent pairs, every GPU holds the whole sequence store,
-// only results are gathered, so there is no collective.  Pairs are assigned longest-processing-time-first to the
-// least-loaded GPU by predicted cost ~ wavefront cells = (max(len) * divergence + |len difference|)^2.
+// only results are gathered, so there is no collective.  Predicted cost of a pair ~ wavefront cells ~ (expected score)^2 with
+// expected score = length x divergence (+ the length difference, which is a forced gap); the divergence comes from the GPU's
+// stranded sketches (aw_estimate_divergence) when available.
 inline double predicted_pair_cost(uint64_t len_q, uint64_t len_t, double divergence = 0.05) {
-    const double s = (double)std::max(len_q, len_t) * std::max(divergence, 1e-4) + (double)(len_q > len_t ? len_q - len_t : len_t - len_q);
+    const double s = (double)std::max(len_q, len_t) * std::min(0.5, std::max(divergence, 1e-3)) + (double)(len_q > len_t ? len_q - len_t : len_t - len_q);
     return s * s + (double)(len_q + len_t);
 }
-// returns n_parts lists of indices into `pairs`, each ascending; deterministic
+// static longest-processing-time-first partition: n_parts lists of indices into `pairs`, each ascending; deterministic.
+// (The drivers below use a shared queue of cost-ordered chunks instead, which also absorbs mispredicted costs; the static
+// partition remains for callers that must know the shards up front, e.g. one process per GPU.)
 inline std::vector<std::vector<size_t>> partition_pairs(const std::vector<std::pair<size_t, size_t>>& pairs, const std::vector<Sequence>& seqs,
-                                                        size_t n_parts) {
+                                                        size_t n_parts, const std::vector<float>* divergence = nullptr) {
     std::vector<std::vector<size_t>> shards(std::max<size_t>(1, n_parts));
     if (n_parts <= 1) {
         shards[0].resize(pairs.size());
@@ -388,7 +396,8 @@ inline std::vector<std::vector<size_t>> partition_pairs(const std::vector<std::p
         return shards;
     }
     std::vector<std::pair<double, size_t>> costed(pairs.size());
-    for (size_t i = 0; i < pairs.size(); ++i) costed[i] = {predicted_pair_cost(seqs[pairs[i].first].seq.size(), seqs[pairs[i].second].seq.size()), i};
+    for (size_t i = 0; i < pairs.size(); ++i)
+        costed[i] = {predicted_pair_cost(seqs[pairs[i].first].seq.size(), seqs[pairs[i].second].seq.size(), divergence ? (double)(*divergence)[i] : 0.05), i};
     std::sort(costed.begin(), costed.end(), [](const auto& a, const auto& b) { return a.first != b.first ? a.first > b.first : a.second < b.second; });
     std::vector<double> load(n_parts, 0.0);
     for (const auto& c : costed) {
@@ -403,71 +412,58 @@ inline std::vector<std::vector<size_t>> partition_pairs(const std::vector<std::p
 class AllPairIterator {
    public:
     // AllPairIterator::new (src/iterator.rs:25-28) == with_options(seqs, params, true, false, None)
+    AllPairIterator(Context& ctx, const std::vector<Sequence>& sequences, const AlignmentParams& params)
+        : AllPairIterator(ctx, sequences, params, true, false, SparsificationStrategy()) {}
     // with_options (src/iterator.rs:30-92); the sequences must already be loaded into ctx
-    // (optimize("O0"): g++ 13.3 segfaults in its GIMPLE ccp pass on this constructor at -O1 and above)
-    __attribute__((optimize("O0"))) AllPairIterator(Context& ctx, const std::vector<Sequence>& sequences, const AlignmentParams& params,
-                                                   bool exclude_self = true, bool use_mash_orientation = false,
-                                                   const SparsificationStrategy& sp = SparsificationStrategy())
+    AllPairIterator(Context& ctx, const std::vector<Sequence>& sequences, const AlignmentParams& params, bool exclude_self, bool use_mash_orientation,
+                    const SparsificationStrategy& sp)
         : ctx_(ctx), seqs_(sequences), params_(params), orientation_params_(AlignmentParams::edit_distance()), exclude_self_(exclude_self),
-          use_mash_(use_mash_orientation), pairs_(build_pair_list(ctx, sequences, exclude_self, sp)) {}
+          use_mash_(use_mash_orientation) {
+        pairs_ = build_pair_list(ctx, sequences, exclude_self, sp);
+    }
     AllPairIterator& with_orientation_params(AlignmentParams p) {
         orientation_params_ = std::move(p);
         return *this;
     }
     size_t pair_count() const { return pairs_.size(); }
+    // keeps the first n pairs of the list (benchmarks on a bounded, deterministic prefix of a huge job)
+    void truncate(size_t n) {
+        if (n < pairs_.size()) pairs_.resize(n);
+    }
     const std::vector<std::pair<size_t, size_t>>& get_pairs() const { return pairs_; }
 
-    // for_each_with_callback (src/iterator.rs:127-137,208-252): the whole remaining pair list goes to the GPU
-    void for_each_with_callback(const Callback& cb, uint32_t flags = 0) {
-        run(next_, pairs_.size() - next_, cb, flags);
-        next_ = pairs_.size();
+    // for_each_with_callback (src/iterator.rs:127-137,208-252): the whole remaining pair list goes to the GPU(s).
+    // `others` are further contexts (GPUs) that hold the same sequences.  The callback may throw: the first exception
+    // cancels the run on every GPU (no further chunk is started, chunks in flight are dropped) and is rethrown here,
+    // like the reference's first-error capture.
+    void for_each_with_callback(const Callback& cb, uint32_t flags = 0, const std::vector<Context*>& others = {}) {
+        Delivery d;
+        d.cb = &cb;
+        drive(d, flags, others);
     }
-    // PAF-only fast path of the CLI writer (src/main.rs:347-374): hands out the GPU-formatted line without building an
-    // AlignmentResult (three heap strings per pair dominate the host time on short-read workloads)
+    void for_each_with_callback_multi(const std::vector<Context*>& others, const Callback& cb, uint32_t flags = 0) { for_each_with_callback(cb, flags, others); }
+    // PAF writer paths of the CLI (src/main.rs:347-374).  Blocks: newline-terminated PAF lines exactly as they leave the
+    // GPU (within a block the lines are in pair order; with one GPU the blocks are too), no per-pair host work at all.
+    using BlockCallback = std::function<void(const char* text, size_t len, size_t n_lines)>;
+    void for_each_paf_block(const BlockCallback& cb, const std::vector<Context*>& others = {}) {
+        Delivery d;
+        d.block = &cb;
+        drive(d, AW_FLAG_PAF_BLOCKS, others);
+    }
+    // one call per line (without the newline)
     using PafCallback = std::function<void(const char*, size_t)>;
     void for_each_paf(const PafCallback& cb, const std::vector<Context*>& others = {}) {
-        const Callback adapt = [&](const AlignmentResult& r) { cb(r.paf.data(), r.paf.size()); };
-        paf_only_ = &cb;
-        try {
-            if (others.empty()) for_each_with_callback(adapt);
-            else for_each_with_callback_multi(others, adapt);
-        } catch (...) {
-            paf_only_ = nullptr;
-            throw;
-        }
-        paf_only_ = nullptr;
-    }
-    // the same over several GPUs: `others` are further contexts that hold the same sequences; one host thread per GPU
-    // aligns its shard of the remaining pair list, the callback is serialised (completion order, like the reference's
-    // rayon workers), the first callback / device error cancels that GPU's shard and is rethrown after the join
-    void for_each_with_callback_multi(const std::vector<Context*>& others, const Callback& cb, uint32_t flags = 0) {
-        std::vector<Context*> ctxs{&ctx_};
-        ctxs.insert(ctxs.end(), others.begin(), others.end());
-        std::vector<std::pair<size_t, size_t>> rest(pairs_.begin() + next_, pairs_.end());
-        next_ = pairs_.size();
-        const auto shards = partition_pairs(rest, seqs_, ctxs.size());
-        std::mutex mu;
-        std::vector<std::exception_ptr> errs(ctxs.size());
-        const Callback locked = [&](const AlignmentResult& r) {
-            std::lock_guard<std::mutex> g(mu);
-            cb(r);
+        const BlockCallback split = [&](const char* text, size_t len, size_t) {
+            const char* p = text;
+            const char* end = text + len;
+            while (p < end) {
+                const char* nl = (const char*)std::memchr(p, '\n', (size_t)(end - p));
+                if (!nl) nl = end;
+                cb(p, (size_t)(nl - p));
+                p = nl + 1;
+            }
         };
-        paf_mu_ = &mu;
-        std::vector<std::thread> th;
-        for (size_t g = 0; g < ctxs.size(); ++g)
-            th.emplace_back([&, g] {
-                try {
-                    std::vector<std::pair<size_t, size_t>> mine(shards[g].size());
-                    for (size_t i = 0; i < mine.size(); ++i) mine[i] = rest[shards[g][i]];
-                    run_on(*ctxs[g], mine, 0, mine.size(), locked, flags);
-                } catch (...) {
-                    errs[g] = std::current_exception();
-                }
-            });
-        for (auto& t : th) t.join();
-        paf_mu_ = nullptr;
-        for (auto& e : errs)
-            if (e) std::rethrow_exception(e);
+        for_each_paf_block(split, others);
     }
     // impl Iterator::next (src/iterator.rs:151-171): strictly in pair order; batches are prefetched
     std::optional<AlignmentResult> next() {
@@ -476,37 +472,60 @@ class AllPairIterator {
             buf_pos_ = 0;
             if (next_ >= pairs_.size()) return std::nullopt;
             const size_t cnt = std::min<size_t>(prefetch_, pairs_.size() - next_);
-            run(next_, cnt, [&](const AlignmentResult& r) { buffered_.push_back(r); }, 0);
-            next_ += cnt;
+            const Callback keep = [&](const AlignmentResult& r) { buffered_.push_back(r); };
+            Delivery d;
+            d.cb = &keep;
+            const size_t saved_end = limit_;
+            limit_ = next_ + cnt;
+            try {
+                drive(d, 0, {});
+            } catch (...) {
+                limit_ = saved_end;
+                throw;
+            }
+            limit_ = saved_end;
         }
         return buffered_[buf_pos_++];
     }
     void set_prefetch(size_t n) { prefetch_ = n ? n : 1; }
+    // pairs per chunk handed to a GPU at a time (0 = automatic)
+    void set_chunk_pairs(size_t n) { chunk_pairs_ = n; }
+    // max / mean of the per-GPU busy time of the last multi-GPU run (1.0 = perfectly balanced)
+    double last_imbalance() const { return last_imbalance_; }
 
    private:
-    struct Trampoline {
-        const Callback* cb;
-        std::exception_ptr err;
-        uint32_t flags;
-        const PafCallback* paf_only;
-        std::mutex* mu;
+    struct Delivery {
+        const Callback* cb = nullptr;
+        const BlockCallback* block = nullptr;
     };
+    // one per run, shared by all GPU threads: the cost-ordered pair list, the chunk cursor, the first error
+    struct Shared {
+        std::vector<aw_pair> pairs;
+        size_t chunk = 65536;
+        std::atomic<size_t> next{0};
+        std::atomic<bool> cancel{false};
+        std::mutex mu;  // serialises the user's callback (completion order, like the reference's rayon workers) and `err`
+        std::exception_ptr err;
+        Delivery d;
+        uint32_t flags = 0;
+    };
+    static uint64_t next_chunk(void* user, const aw_pair** out) {
+        Shared* sh = static_cast<Shared*>(user);
+        if (sh->cancel.load(std::memory_order_relaxed)) return 0;
+        const size_t b = sh->next.fetch_add(sh->chunk);
+        if (b >= sh->pairs.size()) return 0;
+        *out = sh->pairs.data() + b;
+        return std::min(sh->chunk, sh->pairs.size() - b);
+    }
+    static int fail(Shared* sh) {
+        std::lock_guard<std::mutex> g(sh->mu);  // callers hold no lock
+        if (!sh->err) sh->err = std::current_exception();
+        sh->cancel.store(true);
+        return 1;
+    }
     static int c_callback(const aw_result* r, void* user) {
-        Trampoline* t = static_cast<Trampoline*>(user);
-        if (t->paf_only) {
-            try {
-                if (t->mu) {
-                    std::lock_guard<std::mutex> g(*t->mu);
-                    (*t->paf_only)(r->paf, r->paf_len);
-                } else {
-                    (*t->paf_only)(r->paf, r->paf_len);
-                }
-            } catch (...) {
-                t->err = std::current_exception();
-                return 1;
-            }
-            return 0;
-        }
+        Shared* sh = static_cast<Shared*>(user);
+        if (sh->cancel.load(std::memory_order_relaxed)) return 1;
         AlignmentResult a;
         a.query_idx = r->query_idx;
         a.target_idx = r->target_idx;
@@ -522,40 +541,108 @@ class AllPairIterator {
         if (r->cg) a.cigar.assign(r->cg, r->cg_len);
         if (r->paf) a.paf.assign(r->paf, r->paf_len);
         try {
-            (*t->cb)(a);
+            std::lock_guard<std::mutex> g(sh->mu);
+            if (sh->cancel.load()) return 1;
+            (*sh->d.cb)(a);
         } catch (...) {
-            t->err = std::current_exception();
-            return 1;
+            return fail(sh);
         }
         return 0;
     }
-    void run(size_t first, size_t count, const Callback& cb, uint32_t flags) { run_on(ctx_, pairs_, first, count, cb, flags); }
-    void run_on(Context& ctx_, const std::vector<std::pair<size_t, size_t>>& pairs_, size_t first, size_t count, const Callback& cb, uint32_t flags) {
-        if (count == 0) return;
-        std::vector<aw_pair> cp(count);
-        for (size_t i = 0; i < count; ++i) {
-            cp[i].query_idx = (uint32_t)pairs_[first + i].first;
-            cp[i].target_idx = (uint32_t)pairs_[first + i].second;
+    static int c_block(const char* text, uint64_t len, uint64_t n_lines, void* user) {
+        Shared* sh = static_cast<Shared*>(user);
+        if (sh->cancel.load(std::memory_order_relaxed)) return 1;
+        try {
+            std::lock_guard<std::mutex> g(sh->mu);
+            if (sh->cancel.load()) return 1;
+            (*sh->d.block)(text, (size_t)len, (size_t)n_lines);
+        } catch (...) {
+            return fail(sh);
         }
+        return 0;
+    }
+    // the parallel driver (src/iterator.rs:208-252): one host thread per GPU pulls chunks from the shared queue and streams
+    // them through aw_align_stream (two batches in flight per GPU).  With several GPUs the list is first ordered by
+    // predicted cost, heaviest first, so that the chunks handed out last are the cheap ones.
+    void drive(const Delivery& d, uint32_t flags, const std::vector<Context*>& others) {
+        std::vector<Context*> ctxs{&ctx_};
+        ctxs.insert(ctxs.end(), others.begin(), others.end());
+        const size_t first = next_, last = std::min(limit_, pairs_.size());
+        next_ = last;
+        if (first >= last) return;
+        Shared sh;
+        sh.d = d;
+        sh.flags = flags;
+        sh.pairs.resize(last - first);
+        for (size_t i = first; i < last; ++i) sh.pairs[i - first] = aw_pair{(uint32_t)pairs_[i].first, (uint32_t)pairs_[i].second};
+        const size_t n = sh.pairs.size(), g_n = ctxs.size();
         const aw_params p = params_.to_c();
         if (!use_mash_) {
             const aw_params op = orientation_params_.to_c();
-            int rco = aw_set_orientation_params(ctx_.get(), &op);
-            if (rco != AW_OK) throw std::runtime_error(std::string("aw_set_orientation_params: ") + aw_strerror(rco) + ": " + aw_last_error());
+            for (Context* c : ctxs) {
+                int rco = aw_set_orientation_params(c->get(), &op);
+                if (rco != AW_OK) throw std::runtime_error(std::string("aw_set_orientation_params: ") + aw_strerror(rco) + ": " + aw_last_error());
+            }
         }
-        Trampoline t{&cb, nullptr, flags, paf_only_, paf_mu_};
-        int rc = aw_align_pairs(ctx_.get(), &p, use_mash_ ? AW_ORIENT_MASH : AW_ORIENT_WFA, cp.data(), count, flags, &c_callback, &t);
-        if (t.err) std::rethrow_exception(t.err);
-        if (rc != AW_OK) throw std::runtime_error(std::string("aw_align_pairs: ") + aw_strerror(rc) + ": " + aw_last_error());
+        if (g_n > 1) {
+            std::vector<float> div;
+            if (use_mash_) {
+                div.resize(n);
+                int rc = aw_estimate_divergence(ctx_.get(), sh.pairs.data(), n, div.data());
+                if (rc != AW_OK) throw std::runtime_error(std::string("aw_estimate_divergence: ") + aw_strerror(rc) + ": " + aw_last_error());
+            }
+            std::vector<std::pair<double, uint32_t>> costed(n);
+            for (size_t i = 0; i < n; ++i)
+                costed[i] = {predicted_pair_cost(seqs_[sh.pairs[i].query_idx].seq.size(), seqs_[sh.pairs[i].target_idx].seq.size(), div.empty() ? 0.05 : (double)div[i]),
+                             (uint32_t)i};
+            std::stable_sort(costed.begin(), costed.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+            std::vector<aw_pair> ordered(n);
+            for (size_t i = 0; i < n; ++i) ordered[i] = sh.pairs[costed[i].second];
+            sh.pairs.swap(ordered);
+        }
+        // chunk size: large enough to fill a GPU many times over, small enough that every GPU gets >= ~12 chunks
+        // (a launch should carry >= ~8 pairs per resident CTA, or reads by the hundred thousand, to keep its tail short)
+        size_t max_len = 0;
+        for (const auto& s : seqs_) max_len = std::max(max_len, s.seq.size());
+        const size_t lo = max_len <= 1024 ? 65536 : 4736, hi = max_len <= 1024 ? 262144 : 65536;
+        sh.chunk = chunk_pairs_ ? chunk_pairs_ : std::min<size_t>(hi, std::max<size_t>(lo, (n + 12 * g_n - 1) / (12 * g_n)));
+        std::vector<double> busy(g_n, 0.0);
+        std::vector<int> rcs(g_n, AW_OK);
+        std::vector<std::string> msgs(g_n);
+        auto work = [&](size_t g) {
+            const auto t0 = std::chrono::steady_clock::now();
+            rcs[g] = aw_align_stream(ctxs[g]->get(), &p, use_mash_ ? AW_ORIENT_MASH : AW_ORIENT_WFA, flags, &next_chunk, &sh, d.cb ? &c_callback : nullptr,
+                                     d.block ? &c_block : nullptr, &sh);
+            if (rcs[g] != AW_OK && rcs[g] != AW_ECALLBACK) {
+                msgs[g] = std::string("aw_align_stream: ") + aw_strerror(rcs[g]) + ": " + aw_last_error();
+                sh.cancel.store(true);  // a device error on one GPU stops the others too
+            }
+            busy[g] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        };
+        if (g_n == 1) {
+            work(0);
+        } else {
+            std::vector<std::thread> th;
+            for (size_t g = 0; g < g_n; ++g) th.emplace_back(work, g);
+            for (auto& t : th) t.join();
+        }
+        double mx = 0.0, sum = 0.0;
+        for (double b : busy) {
+            mx = std::max(mx, b);
+            sum += b;
+        }
+        last_imbalance_ = sum > 0.0 ? mx / (sum / (double)g_n) : 1.0;
+        if (sh.err) std::rethrow_exception(sh.err);
+        for (size_t g = 0; g < g_n; ++g)
+            if (rcs[g] != AW_OK && rcs[g] != AW_ECALLBACK) throw std::runtime_error(msgs[g]);
     }
     Context& ctx_;
     const std::vector<Sequence>& seqs_;
     AlignmentParams params_, orientation_params_;
     bool exclude_self_, use_mash_;
     std::vector<std::pair<size_t, size_t>> pairs_;
-    const PafCallback* paf_only_ = nullptr;
-    std::mutex* paf_mu_ = nullptr;
-    size_t next_ = 0, prefetch_ = 4096, buf_pos_ = 0;
+    size_t next_ = 0, limit_ = (size_t)-1, prefetch_ = 4096, buf_pos_ = 0, chunk_pairs_ = 0;
+    double last_imbalance_ = 1.0;
     std::vector<AlignmentResult> buffered_;
 };
 

@@ -1,7 +1,7 @@
 // allwave_cli.cpp -- minimal driver with allwave's CLI surface for the alignment path
 // (src/main.rs:32-80): -i FASTA[.gz] [-o PAF] [-s scores | -x ANI preset] [-p strategy] [-t N] [-k prefixes | -e prefixes]
-// [--mash-matrix] [--wfa-orientation] [--no-progress] [--gpu D] [--gpus N].  FASTA parsing and the PAF writer stay on the
-// host; everything between the pair list and the PAF text runs on the GPU through liballwave_cuda.so.
+// [--mash-matrix] [--wfa-orientation] [--no-progress] [--gpu D] [--gpus N].  FASTA parsing and the PAF writer thread stay on
+// the host; everything between the pair list and the ready-to-write PAF text runs on the GPU through liballwave_cuda.so.
 #include <chrono>
 #include <cstdio>
 #include <iostream>
@@ -9,10 +9,60 @@
 
 #include "allwave.hpp"
 
+// bounded single-consumer queue + writer thread (src/main.rs:347-367)
+class PafWriter {
+   public:
+    explicit PafWriter(FILE* out) : out_(out), th_([this] { run(); }) {}
+    ~PafWriter() { close(); }
+    void push(const char* text, size_t len) {
+        std::string blk(text, len);
+        std::unique_lock<std::mutex> g(mu_);
+        not_full_.wait(g, [&] { return bytes_ < kMaxBytes; });
+        bytes_ += blk.size();
+        q_.push_back(std::move(blk));
+        not_empty_.notify_one();
+    }
+    void close() {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            if (closed_) return;
+            closed_ = true;
+        }
+        not_empty_.notify_one();
+        th_.join();
+        if (failed_) throw std::runtime_error("error while writing the PAF output");
+    }
+
+   private:
+    void run() {
+        for (;;) {
+            std::string blk;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                not_empty_.wait(g, [&] { return !q_.empty() || closed_; });
+                if (q_.empty()) return;
+                blk = std::move(q_.front());
+                q_.pop_front();
+                bytes_ -= blk.size();
+            }
+            not_full_.notify_one();
+            if (std::fwrite(blk.data(), 1, blk.size(), out_) != blk.size()) failed_ = true;
+        }
+    }
+    static constexpr size_t kMaxBytes = 1ull << 30;
+    FILE* out_;
+    std::mutex mu_;
+    std::condition_variable not_empty_, not_full_;
+    std::deque<std::string> q_;
+    size_t bytes_ = 0;
+    bool closed_ = false, failed_ = false;
+    std::thread th_;
+};
+
 int main(int argc, char** argv) {
     std::string input, output, scores = "0,5,8,2,24,1", spars = "giant:0.99", preset, keep_prefixes, exclude_prefixes;
     bool wfa_orientation = false, progress = true, mash_matrix = false, scores_given = false;
-    int device = 0, gpus = 1;
+    int device = 0, gpus = 1, threads = 1;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto need = [&](const char* name) -> std::string {
@@ -32,7 +82,7 @@ int main(int argc, char** argv) {
         else if (a == "-e" || a == "--exclude-prefixes") exclude_prefixes = need("-e");
         else if (a == "--mash-matrix") mash_matrix = true;
         else if (a == "-p" || a == "--sparsification") spars = need("-p");
-        else if (a == "-t" || a == "--threads") (void)need("-t");  // host threads are irrelevant: pairs run on the GPU
+        else if (a == "-t" || a == "--threads") threads = std::max(1, std::atoi(need("-t").c_str()));
         else if (a == "--gpu") device = std::atoi(need("--gpu").c_str());
         else if (a == "--gpus") gpus = std::max(1, std::atoi(need("--gpus").c_str()));  // devices device .. device+gpus-1, pairs sharded by predicted cost
         else if (a == "--wfa-orientation") wfa_orientation = true;
@@ -52,6 +102,10 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "error: the argument '--keep-prefixes <KEEP_PREFIXES>' cannot be used with '--exclude-prefixes <EXCLUDE_PREFIXES>'\n");
         return 2;
     }
+    // -t: the reference's rayon pool size.  Here the pairs run on the GPU(s); the host always uses one driver thread per GPU
+    // plus one writer thread, so -t only matters as "more than one worker": it allows cost-ordered (out-of-order) scheduling
+    // on a single GPU exactly like --gpus N does (the reference's output order is unspecified for -t > 1 as well).
+    (void)threads;
     if (input.empty()) {
         std::fprintf(stderr, "error: -i/--input is required\n");
         return 2;
@@ -105,14 +159,17 @@ int main(int argc, char** argv) {
         FILE* out = output.empty() ? stdout : std::fopen(output.c_str(), "w");
         if (!out) throw std::runtime_error("cannot open " + output);
         const auto t0 = std::chrono::steady_clock::now();
+        // the writer has its own thread fed through a bounded queue, like the reference's mpsc writer (src/main.rs:347-367):
+        // file I/O overlaps the GPUs and the D2H copies; the GPU threads only move a block pointer
+        PafWriter writer(out);
         size_t done = 0;
-        it.for_each_paf(
-            [&](const char* line, size_t len) {
-                std::fwrite(line, 1, len, out);
-                std::fputc('\n', out);
-                ++done;
+        it.for_each_paf_block(
+            [&](const char* text, size_t len, size_t n_lines) {
+                writer.push(text, len);
+                done += n_lines;
             },
             others);
+        writer.close();
         if (out != stdout) std::fclose(out);
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (progress) std::fprintf(stderr, "[%.1fs] %zu/%zu (100.0%%) %.1f alignments/sec - Complete!\n", dt, done, it.pair_count(), done / std::max(dt, 1e-9));

@@ -1,7 +1,9 @@
 // host_capi.cpp -- C exports of the C++ host mirror (allwave.hpp) so that tests written in
 // Python can check pair scheduling and flag parsing against the oracle.
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 
 #include "allwave.hpp"
 
@@ -150,6 +152,103 @@ int64_t awh_read_fasta(const char* path, const char* keep, const char* exclude, 
         g_msg = e.what();
         return -1;
     }
+}
+
+// The whole host path on in-memory sequences over `n_gpus` devices (first_device ..): contexts, sequence upload, pair list
+// (-p grammar), the streaming multi-GPU driver, PAF blocks to `out_path` (NULL/"" = discard).  This is what `allwave --gpus N`
+// does after reading the FASTA; bench.py uses it for the strong-scaling run through the product path.
+//   max_pairs > 0 truncates the pair list (deterministic prefix);  checksum != 0 adds an order-independent digest of the lines
+//   out[0] pairs, out[1] PAF bytes, out[2] seconds (alignment: pair list ready -> last byte delivered), out[3] seconds (setup:
+//   contexts + upload + pair list), out[4] max/mean GPU busy time, out[5] digest (sum of per-line FNV-1a hashes, as double bits)
+int awh_run_job(uint64_t n, const char* const* ids, const uint8_t* const* seqs, const uint64_t* lens, const char* scores, const char* spars, int use_mash,
+                int first_device, int n_gpus, uint64_t max_pairs, const char* out_path, int checksum, double* out) {
+    try {
+        std::vector<Sequence> S(n);
+        for (uint64_t i = 0; i < n; ++i) {
+            S[i].id = ids[i];
+            S[i].seq.assign(seqs[i], seqs[i] + lens[i]);
+        }
+        const auto t0 = std::chrono::steady_clock::now();
+        std::vector<std::unique_ptr<Context>> ctxs((size_t)std::max(1, n_gpus));
+        {
+            std::vector<std::thread> th;
+            std::vector<std::exception_ptr> errs(ctxs.size());
+            for (size_t g = 0; g < ctxs.size(); ++g)
+                th.emplace_back([&, g] {
+                    try {
+                        ctxs[g].reset(new Context(first_device + (int)g));
+                        ctxs[g]->load(S);
+                    } catch (...) {
+                        errs[g] = std::current_exception();
+                    }
+                });
+            for (auto& t : th) t.join();
+            for (auto& e : errs)
+                if (e) std::rethrow_exception(e);
+        }
+        std::vector<Context*> others;
+        for (size_t g = 1; g < ctxs.size(); ++g) others.push_back(ctxs[g].get());
+        AllPairIterator it(*ctxs[0], S, parse_scores(scores), true, use_mash != 0, parse_sparsification(spars));
+        if (max_pairs) it.truncate(max_pairs);
+        FILE* f = (out_path && *out_path) ? std::fopen(out_path, "w") : nullptr;
+        if (out_path && *out_path && !f) throw std::runtime_error(std::string("cannot open ") + out_path);
+        const auto t1 = std::chrono::steady_clock::now();
+        uint64_t bytes = 0, lines = 0, digest = 0;
+        it.for_each_paf_block(
+            [&](const char* text, size_t len, size_t n_lines) {
+                bytes += len;
+                lines += n_lines;
+                if (f) std::fwrite(text, 1, len, f);
+                if (checksum) {
+                    uint64_t h = 1469598103934665603ull;
+                    for (size_t i = 0; i < len; ++i) {
+                        if (text[i] == '\n') {
+                            digest += h;
+                            h = 1469598103934665603ull;
+                        } else {
+                            h = (h ^ (uint8_t)text[i]) * 1099511628211ull;
+                        }
+                    }
+                }
+            },
+            others);
+        const auto t2 = std::chrono::steady_clock::now();
+        if (f) std::fclose(f);
+        out[0] = (double)lines;
+        out[1] = (double)bytes;
+        out[2] = std::chrono::duration<double>(t2 - t1).count();
+        out[3] = std::chrono::duration<double>(t1 - t0).count();
+        out[4] = it.last_imbalance();
+        std::memcpy(&out[5], &digest, 8);
+        return 0;
+    } catch (const std::exception& e) {
+        g_msg = e.what();
+        return -1;
+    }
+}
+
+// callback-error cancellation (src/iterator.rs:235-251) through the C++ wrapper: the callback throws at its
+// `fail_at`-th result; returns the number of results delivered before the run stopped, -1 if nothing was thrown back
+int64_t awh_test_cancel(aw_ctx* ctx, uint64_t n, const char* const* ids, const uint64_t* lens, uint64_t fail_at, uint64_t chunk_pairs, char* msg_out /*>=128*/) {
+    std::vector<Sequence> S(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        S[i].id = ids[i];
+        S[i].seq.resize(lens[i]);  // lengths only: the sequences are already loaded in ctx
+    }
+    Context c(ctx, false);
+    AllPairIterator it(c, S, AlignmentParams(), true, true, SparsificationStrategy::none());
+    it.set_chunk_pairs(chunk_pairs);
+    uint64_t seen = 0;
+    try {
+        it.for_each_with_callback([&](const AlignmentResult&) {
+            if (++seen == fail_at) throw std::runtime_error("callback failed on purpose");
+        });
+    } catch (const std::exception& e) {
+        std::strncpy(msg_out, e.what(), 127);
+        msg_out[127] = 0;
+        return (int64_t)seen;
+    }
+    return -1;
 }
 
 void awh_free(void* p) { std::free(p); }

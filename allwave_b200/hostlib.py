@@ -36,6 +36,10 @@ def lib():
         L.awh_parse_ani_preset.argtypes = [C.c_char_p, C.c_char_p]
         L.awh_read_fasta.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         L.awh_read_fasta.restype = C.c_int64
+        L.awh_run_job.argtypes = [C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                                  C.c_int, C.c_uint64, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
+        L.awh_test_cancel.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.c_char_p]
+        L.awh_test_cancel.restype = C.c_int64
         L.awh_partition_pairs.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
@@ -112,3 +116,32 @@ def read_fasta(path, keep_prefixes="", exclude_prefixes=""):
     joined = C.string_at(ids.value).decode()
     lib().awh_free(ids)
     return [x for x in joined.split("\n") if x != ""][:n] if n else [], tot.value
+
+
+def run_job(ids, seqs, scores="0,5,8,2,24,1", sparsification="none", use_mash=True, first_device=0, n_gpus=1, max_pairs=0, out_path="", checksum=False):
+    """the product path of `allwave --gpus N` on in-memory sequences (host_capi.cpp awh_run_job): contexts on n_gpus devices,
+    pair list, streaming multi-GPU driver, PAF blocks.  Returns a dict with pairs, paf_bytes, seconds, setup_seconds,
+    imbalance (max/mean GPU busy time) and, with checksum=True, an order-independent digest of the PAF lines."""
+    n = len(seqs)
+    ia = (C.c_char_p * max(1, n))(*[i.encode() for i in ids])
+    sa = (C.c_char_p * max(1, n))(*seqs)
+    la = (C.c_uint64 * max(1, n))(*[len(s) for s in seqs])
+    out = (C.c_double * 6)()
+    rc = lib().awh_run_job(n, ia, sa, la, scores.encode(), sparsification.encode(), 1 if use_mash else 0, first_device, n_gpus, max_pairs,
+                           str(out_path).encode(), 1 if checksum else 0, out)
+    if rc != 0:
+        raise RuntimeError(lib().awh_last_message().decode())
+    import struct
+
+    digest = struct.unpack("<Q", struct.pack("<d", out[5]))[0]
+    return dict(pairs=int(out[0]), paf_bytes=int(out[1]), seconds=out[2], setup_seconds=out[3], imbalance=out[4], digest=digest)
+
+
+def cancel_probe(ctx, ids, lens, fail_at, chunk_pairs=0):
+    """for_each_with_callback whose callback throws at result `fail_at`: (results seen, message) or (-1, "") if nothing was rethrown"""
+    n = len(ids)
+    ia = (C.c_char_p * max(1, n))(*[i.encode() for i in ids])
+    la = (C.c_uint64 * max(1, n))(*lens)
+    msg = C.create_string_buffer(128)
+    seen = lib().awh_test_cancel(ctx._h, n, ia, la, fail_at, chunk_pairs, msg)
+    return seen, msg.value.decode()

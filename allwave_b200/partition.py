@@ -10,19 +10,24 @@ import heapq
 
 
 def predicted_cost(len_q, len_t, divergence=None):
-    d = 0.05 if divergence is None else max(divergence, 1e-4)
+    d = 0.05 if divergence is None else min(0.5, max(divergence, 1e-3))
     s = max(len_q, len_t) * d + abs(len_q - len_t)
     return s * s + (len_q + len_t)
 
 
 def partition_pairs(pairs, lens, n_parts, divergence=None):
-    """pairs: list of (q, t); lens: sequence lengths; divergence: optional dict {(q,t): d}.
-    Returns n_parts lists; every pair appears exactly once; deterministic."""
+    """pairs: list of (q, t); lens: sequence lengths; divergence: optional dict {(q,t): d} or list aligned with pairs
+    (Context.estimate_divergence).  Returns n_parts lists; every pair appears exactly once; deterministic."""
     if n_parts <= 1:
         return [list(pairs)]
     costed = []
     for idx, (q, t) in enumerate(pairs):
-        d = divergence.get((q, t)) if divergence else None
+        if divergence is None:
+            d = None
+        elif isinstance(divergence, dict):
+            d = divergence.get((q, t))
+        else:
+            d = divergence[idx]
         costed.append((predicted_cost(lens[q], lens[t], d), idx))
     costed.sort(key=lambda x: (-x[0], x[1]))
     heap = [(0.0, r) for r in range(n_parts)]

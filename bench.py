@@ -1,23 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- aligned pairs/s of the allwave alignment hot path on B200 (BASELINE.json metric).
 
-Workload (config.workload): BASELINE config 2 -- 1,000 x 10 kb synthetic sequences at 5 %
-per-haplotype divergence, `-p none` (999,000 directed pairs), scores 0,5,8,2,24,1, mash
-orientation.  A "step" is one pass of the whole hot path (orientation -> biWFA -> CIGAR ->
-PAF text) over one batch of `--batch` pairs per GPU drawn from that pair list; every rank
-aligns its own shard (weak scaling, no collective on the data path).
+Default workload (config.workload): BASELINE config 2 -- 1,000 x 10 kb synthetic sequences at 5 % per-haplotype
+divergence, `-p none` (999,000 directed pairs), scores 0,5,8,2,24,1, mash orientation.  `--config C1..C5` selects the
+other BASELINE configs (SURVEY 8d generator, same seeds).  A "step" is one pass of the whole hot path (orientation ->
+biWFA -> CIGAR -> PAF text) over one batch of `--batch` pairs per GPU drawn from that config's pair list.
 
-  value     device-resident: sequences + pair list already in HBM, kernels launched on the
-            timed stream, PAF text left in HBM.
-  e2e       through the host-facing C-ABI call (aw_load_sequences + aw_align_pairs) with HOST
+  --scaling weak (default, the driver's contract): every rank aligns its own shard of world*batch pairs, no collective.
+  --scaling strong: ONE process drives the product path (allwave --gpus N = AllPairIterator over N contexts with a shared
+            chunk queue, liballwave_host.so) over a FIXED pair list on --gpus N devices: total pairs / wall time.
+
+  value     device-resident: sequences + pair list already in HBM, kernels launched on the timed stream, PAF text left in HBM.
+  e2e       through the host-facing C-ABI calls the CLI makes (aw_load_sequences + aw_align_stream with PAF blocks) with HOST
             buffers: H2D of sequences and pairs and D2H of every PAF line inside the timed region.
-  roofline  the alignment kernel alone (CUDA events around it on the launch stream) against the
-            measured HBM copy bandwidth, with SURVEY 8(d)'s algorithmic bytes per pair.
+  roofline  the alignment kernel alone (CUDA events around it on the launch stream) against the measured HBM copy
+            bandwidth, with SURVEY 8(d)'s algorithmic bytes per pair.
   cpu_baseline / --impl reference
-            the CPU restatement of the allwave/WFA2 path (oracle/, "port": the Rust reference
-            cannot be built in this image), all host threads, on a bounded sample of the same pairs.
+            the CPU restatement of the allwave/WFA2 path (oracle/, "port": the Rust reference cannot be built in this
+            image), all host threads, on a bounded sample of the same pairs.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -30,8 +33,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-WORKLOAD = "C2: 1000 x 10 kb, 5% divergence per haplotype, -p none (999,000 directed pairs), -s 0,5,8,2,24,1, mash orientation"
-SCORES = (0, 5, 8, 2, 24, 1)
+# per config: description, scores, -p strategy, default pairs per GPU per step, CPU sample (pairs per core), dtype of the wavefront rows
+CONFIGS = {
+    "C1": dict(desc="C1: 16 x 10 kb, 1% divergence per haplotype, -p none (240 directed pairs), -s 0,5,8,2,24,1, mash orientation",
+               scores=(0, 5, 8, 2, 24, 1), spars="none", batch=240, cpu_pairs_per_core=15, dtype="int16"),
+    "C2": dict(desc="C2: 1000 x 10 kb, 5% divergence per haplotype, -p none (999,000 directed pairs), -s 0,5,8,2,24,1, mash orientation",
+               scores=(0, 5, 8, 2, 24, 1), spars="none", batch=9472, cpu_pairs_per_core=8, dtype="int16"),
+    "C3": dict(desc="C3: 1415 x 150 bp reads, 2% divergence, -p none (2,000,810 directed pairs), -s 0,1,1,1, mash orientation",
+               scores=(0, 1, 1, 1, None, None), spars="none", batch=2000810, cpu_pairs_per_core=20000, dtype="int32"),
+    "C4": dict(desc="C4: 200 x 1 Mb haplotypes, 0.1-2% divergence + SVs, -p giant:0.99 (~1,970 pairs), -s 0,5,8,2,24,1, mash orientation",
+               scores=(0, 5, 8, 2, 24, 1), spars="giant:0.99", batch=0, cpu_pairs_per_core=0, dtype="int32"),
+    "C5": dict(desc="C5: 5000 x 5 kb, 3% divergence, 50% reverse-complemented, -p tree:2:1:0.1 (~2.51 M pairs), -s 0,5,8,2,24,1, mash orientation",
+               scores=(0, 5, 8, 2, 24, 1), spars="tree:2:1:0.1", batch=37888, cpu_pairs_per_core=64, dtype="int16"),
+}
 
 
 def parse_args():
@@ -40,28 +54,48 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="pairs per GPU per step (0 = default)")
-    ap.add_argument("--nseq", type=int, default=1000)
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=0, help="weak: pairs per GPU per step (0 = the config's default)")
+    ap.add_argument("--pairs", type=int, default=0, help="strong: pairs of the fixed job (0 = default)")
+    ap.add_argument("--nseq", type=int, default=0, help="number of sequences (0 = the config's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 2)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = steps")
+    ap.add_argument("--out-paf", default="", help="strong: also write the PAF here")
     return ap.parse_args()
 
 
-def c2_sequences(nseq):
+def config_sequences(name, nseq):
     from allwave_b200 import synth
 
-    c, ids, seqs, _ = synth.config("C2", n=nseq)
+    c, ids, seqs, _ = synth.config(name, n=nseq or None)
     return ids, seqs
 
 
-def job_pairs(nseq, total):
-    """deterministic sample of the `-p none` pair list (src/iterator.rs:40-43): every stride-th pair"""
-    npairs_all = nseq * (nseq - 1)
+def config_pair_list(name, ids, seqs, ctx=None):
+    """the config's full directed pair list, exactly what the CLI would align (src/iterator.rs:37-77)"""
+    from allwave_b200 import hostlib as H
+
+    spars = CONFIGS[name]["spars"]
+    n = len(ids)
+    if spars == "none":
+        return None  # implicit: every (i, j), i != j -- sampled arithmetically
+    sp = H.parse_sparsification(spars)
+    return H.pair_list(ids, sp["kind"], value=sp["value"], k_nearest=sp["k_nearest"], k_farthest=sp["k_farthest"], random_fraction=sp["random_fraction"],
+                       kmer_size=sp["kmer_size"], ctx=ctx)
+
+
+def job_pairs(nseq, total, full=None):
+    """deterministic sample of the pair list: every stride-th pair"""
+    npairs_all = nseq * (nseq - 1) if full is None else len(full)
     total = min(total, npairs_all)
-    stride = max(1, npairs_all // total)
+    stride = max(1, npairs_all // max(1, total))
     out = []
     for t in range(total):
         idx = (t * stride) % npairs_all
+        if full is not None:
+            out.append(tuple(full[idx]))
+            continue
         i, r = divmod(idx, nseq - 1)
         j = r if r < i else r + 1
         out.append((i, j))
@@ -74,6 +108,14 @@ def algorithmic_bytes(seqs, pairs, paf_bytes):
     for q, t in pairs:
         b += (len(seqs[q]) + 3) // 4 + (len(seqs[t]) + 3) // 4 + 16
     return b
+
+
+def kernel_source_hash():
+    """identifies the kernel sources a profile belongs to (profiles/ncu_summary.json carries the same stamp)"""
+    h = hashlib.sha1()
+    for f in ("aw_wfa.cuh", "aw_common.cuh", "aw_sketch.cuh"):
+        h.update(open(os.path.join(ROOT, "allwave_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -123,34 +165,87 @@ class ClockSampler:
         return out
 
 
+def cpu_sample_pairs(cfg, pairs, cores):
+    per_core = CONFIGS[cfg]["cpu_pairs_per_core"]
+    return pairs[: max(2, per_core * cores)] if per_core else []
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU restatement (oracle/) on all host threads; rank 0 only."""
     if rank != 0:
         return
     import oracle_lib as O
 
+    cfg = CONFIGS[args.config]
     cores = os.cpu_count() or 1
-    ids, seqs = c2_sequences(args.nseq)
-    per_step = max(2, 2 * cores)
-    pairs = job_pairs(args.nseq, per_step)
-    p = O.params(*SCORES)
-    for _ in range(args.warmup):
-        O.run_pairs(ids, seqs, pairs[: max(1, cores // 2)], p, use_mash=True, threads=cores)
+    ids, seqs = config_sequences(args.config, args.nseq)
+    if cfg["spars"] == "none":
+        full = None
+    else:  # the pair list of the sparsified configs comes from the oracle here (no GPU on this path)
+        kinds = {"giant": O.SPARS_GIANT, "tree": O.SPARS_TREE}
+        parts = cfg["spars"].split(":")
+        if parts[0] == "giant":
+            full = O.pair_list(ids, seqs, kind=kinds["giant"], fraction=float(parts[1]))
+        else:
+            full = O.pair_list(ids, seqs, kind=kinds["tree"], fraction=float(parts[3]), k_nearest=int(parts[1]), k_farthest=int(parts[2]))
+    per_core = cfg["cpu_pairs_per_core"] or 1
+    per_step = max(2, max(1, per_core // 4) * cores) if args.config != "C4" else 2
+    pairs = job_pairs(len(seqs), per_step, full)
+    p = O.params(*cfg["scores"])
+    for _ in range(min(args.warmup, 1)):
+        O.run_pairs(ids, seqs, pairs[: max(1, min(len(pairs), cores // 2))], p, use_mash=True, threads=cores)
     t0 = time.perf_counter()
     block = 0
     for _ in range(args.steps):
         r = O.run_pairs(ids, seqs, pairs, p, use_mash=True, threads=cores)
         block += r["sum_block_len"]
     dt = time.perf_counter() - t0
-    value = per_step * args.steps / dt
+    value = len(pairs) * args.steps / dt
     line = {
         "impl": "reference", "metric": "aligned pairs/s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step": per_step, "note": "CPU restatement of the allwave/WFA2 path (oracle/); the Rust reference cannot be built here"},
+        "config": {"workload": cfg["desc"], "pairs_per_step": len(pairs),
+                   "note": "CPU restatement of the allwave/WFA2 path (oracle/, PARITY UNPINNED vs WFA2-lib); the Rust reference cannot be built here"},
         "gbp_per_s": block / dt / 1e9,
-        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": f"{per_step} pairs of the C2 pair list per step x {args.steps} steps"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": f"{len(pairs)} pairs of the {args.config} pair list per step x {args.steps} steps"},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_strong(args):
+    """one process, N GPUs, the product path: AllPairIterator::for_each_paf_block over N contexts (shared chunk queue)"""
+    import allwave_b200 as aw
+    from allwave_b200 import hostlib as H
+
+    cfg = CONFIGS[args.config]
+    if aw._cabi.lib().aw_device_count() < args.gpus:
+        raise SystemExit(f"--scaling strong --gpus {args.gpus}: only {aw._cabi.lib().aw_device_count()} devices visible")
+    ids, seqs = config_sequences(args.config, args.nseq)
+    scores = ",".join(str(s) for s in cfg["scores"] if s is not None)
+    default_pairs = {"C1": 240, "C2": 151552, "C3": 2000810, "C4": 64, "C5": 600000}[args.config]
+    max_pairs = args.pairs or default_pairs
+    sampler = ClockSampler(0)
+    runs = []
+    for _ in range(max(1, args.warmup and 1)):  # one warm-up pass on a small prefix: allocations, sketches, instruction caches
+        H.run_job(ids, seqs, scores=scores, sparsification=cfg["spars"], n_gpus=args.gpus, max_pairs=max(1, max_pairs // 16))
+    for _ in range(args.steps):
+        runs.append(H.run_job(ids, seqs, scores=scores, sparsification=cfg["spars"], n_gpus=args.gpus, max_pairs=max_pairs, out_path=args.out_paf))
+    clocks = sampler.stop()
+    chk = H.run_job(ids, seqs, scores=scores, sparsification=cfg["spars"], n_gpus=args.gpus, max_pairs=max_pairs, checksum=True)
+    secs = [r["seconds"] for r in runs]
+    pairs = runs[0]["pairs"]
+    value = pairs * len(runs) / sum(secs)
+    line = {
+        "metric": "aligned pairs/s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * sum(secs) / len(runs), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+        "config": {"workload": cfg["desc"], "pairs_total": pairs, "path": "one process: AllPairIterator::for_each_paf_block over N contexts, shared cost-ordered chunk queue, "
+                   "two batches in flight per GPU, PAF blocks to the host (allwave --gpus N)", "l2": "per-launch working set exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 8 * pairs, "d2h_bytes_per_step": runs[0]["paf_bytes"] + 112 * pairs, "steps": len(runs)},
+        "paf_bytes": runs[0]["paf_bytes"], "paf_digest": "%016x" % chk["digest"], "gpu_imbalance_max_over_mean": max(r["imbalance"] for r in runs),
+        "setup_seconds": runs[0]["setup_seconds"], "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
+        "gpu_launches": None,
     }
     print(json.dumps(line), flush=True)
 
@@ -162,6 +257,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.scaling == "strong":
+        if world > 1:
+            raise SystemExit("--scaling strong is a single-process run: use `python bench.py --scaling strong --gpus N` without torchrun")
+        run_strong(args)
         return
 
     import torch
@@ -176,16 +276,22 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
-    B = args.batch or 9472  # 16 pairs per resident CTA (148 SMs x 4 CTAs): long enough that the last wave's tail is small
-    ids, seqs = c2_sequences(args.nseq)
-    # whole job = world*B pairs; host-side greedy (LPT) partition by predicted cost, no collective
-    job = job_pairs(args.nseq, B * world)
-    shards = partition.partition_pairs(job, [len(s) for s in seqs], world)
-    pairs = shards[rank]
-    params = aw.make_params(*SCORES)
+    cfg = CONFIGS[args.config]
+    scores = cfg["scores"]
+    ids, seqs = config_sequences(args.config, args.nseq)
+    params = aw.make_params(*scores)
 
     ctx = aw.Context(local_rank)
     ctx.load_sequences(ids, seqs)
+    full = config_pair_list(args.config, ids, seqs, ctx)
+    n_all = len(seqs) * (len(seqs) - 1) if full is None else len(full)
+    B = args.batch or cfg["batch"] or (4 * 148)
+    B = min(B, max(1, n_all // world))
+    # whole job = world*B pairs; host-side greedy (LPT) partition by predicted cost (length x estimated divergence), no collective
+    job = job_pairs(len(seqs), B * world, full)
+    div = ctx.estimate_divergence(job) if world > 1 else None
+    shards = partition.partition_pairs(job, [len(s) for s in seqs], world, divergence=div)
+    pairs = shards[rank]
     batch = aw.Batch(ctx, params, pairs, orientation=aw.AW_ORIENT_MASH, flags=0)
     stream = torch.cuda.current_stream()
     sh = stream.cuda_stream
@@ -203,6 +309,7 @@ def main():
     st = batch.stats()
     if st["failed_pairs"]:
         raise SystemExit(f"{st['failed_pairs']} pairs failed on the GPU path")
+    retried = st["pairs_retried"]
     launches_per_step = 2  # orientation kernel + alignment kernel (memsets are not kernels of ours)
 
     # ---- timed: device-resident ----
@@ -222,17 +329,32 @@ def main():
     st = batch.stats()
 
     # ---- timed: end to end through the host-facing C-ABI call, host buffers ----
-    e2e_steps = args.e2e_steps or min(args.steps, 2)
+    e2e_steps = args.e2e_steps or args.steps
     acc = {"paf_bytes": 0, "n": 0}
     import ctypes as C
 
-    def _cb(rp, _u):
-        acc["paf_bytes"] += rp.contents.paf_len
-        acc["n"] += 1
+    # the call the CLI makes: aw_align_stream with AW_FLAG_PAF_BLOCKS -- every batch comes back as one block of
+    # newline-terminated PAF lines in pair order (host memory); the chunks are what aw_align_pairs would cut as well
+    def _blk(text, nbytes, nlines, _u):
+        acc["paf_bytes"] += nbytes - nlines
+        acc["n"] += nlines
         return 0
 
-    cb = aw._cabi.RESULT_CB(_cb)
+    blk = aw._cabi.PAF_BLOCK_CB(_blk)
     arr = aw._cabi.make_pairs(pairs)
+    chunk = 65536
+    cursor = {"pos": 0}
+
+    def _next(_u, out):
+        b = cursor["pos"]
+        if b >= len(pairs):
+            return 0
+        cnt = min(chunk, len(pairs) - b)
+        out[0] = C.cast(C.byref(arr, b * C.sizeof(aw._cabi.AwPair)), C.POINTER(aw._cabi.AwPair))
+        cursor["pos"] = b + cnt
+        return cnt
+
+    src = aw._cabi.CHUNK_SOURCE(_next)
     L = aw._cabi.lib()
     ctx2 = aw.Context(local_rank)
     n = len(seqs)
@@ -244,9 +366,11 @@ def main():
         t_a = time.perf_counter()
         aw._cabi.check(L.aw_load_sequences(ctx2._h, n, sa, la, ia), "aw_load_sequences")
         t_b = time.perf_counter()
-        aw._cabi.check(L.aw_align_pairs(ctx2._h, C.byref(params), aw.AW_ORIENT_MASH, arr, len(pairs), 0, cb, None), "aw_align_pairs")
+        cursor["pos"] = 0
+        aw._cabi.check(L.aw_align_stream(ctx2._h, C.byref(params), aw.AW_ORIENT_MASH, aw.AW_FLAG_PAF_BLOCKS, src, None, C.cast(None, aw._cabi.RESULT_CB), blk, None),
+                       "aw_align_stream")
         if os.environ.get("AW_BENCH_TRACE"):
-            print(f"[e2e] load {1e3 * (t_b - t_a):.1f} ms, align_pairs {1e3 * (time.perf_counter() - t_b):.1f} ms", file=sys.stderr)
+            print(f"[e2e] load {1e3 * (t_b - t_a):.1f} ms, align_stream {1e3 * (time.perf_counter() - t_b):.1f} ms", file=sys.stderr)
 
     e2e_step()  # warm-up (allocations)
     acc.update(paf_bytes=0, n=0)
@@ -282,32 +406,40 @@ def main():
         k_ms = sum(kernel_ms) / len(kernel_ms)
         algo = algorithmic_bytes(seqs, pairs, st["paf_bytes"])
         achieved = algo / (k_ms / 1e3) / 1e9
-        traffic = None
+        # dram bytes of the dominant kernel from the committed ncu capture -- only if it was taken with these kernel sources
+        # and this workload; scaled per pair to the batch of this run
+        traffic, traffic_note = None, "no ncu capture of this kernel build / workload in profiles/ncu_summary.json"
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json"))).get("align_kernel", {}).get("dram_bytes_per_launch")
+            summ = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+            ak = summ.get("align_kernel", {})
+            if summ.get("kernel_source_hash") == kernel_source_hash() and summ.get("config", "C2") == args.config and ak.get("pairs_per_launch"):
+                traffic = ak["dram_bytes_per_launch"] / ak["pairs_per_launch"] * len(pairs)
+                traffic_note = f"ncu --set full capture {summ.get('tag')} ({ak['pairs_per_launch']} pairs per launch), scaled per pair"
         except Exception:
             pass
         line = {
             "metric": "aligned pairs/s", "value": value, "unit": "pairs/s", "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu_per_step": B, "nseq": args.nseq, "partition": f"host LPT over {world} GPUs, no collective",
-                       "l2": "per-launch working set (wavefront rings + history, >10 GB) exceeds the 126 MB L2; no explicit flush"},
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": {"workload": cfg["desc"], "pairs_per_gpu_per_step": len(pairs), "nseq": len(seqs),
+                       "partition": f"host LPT over {world} GPUs by length x estimated divergence, no collective",
+                       "l2": "per-launch working set (wavefront rings + history) exceeds the 126 MB L2; no explicit flush",
+                       "parity_note": "oracle = CPU restatement of WFA2-lib biWFA; PARITY UNPINNED against the real WFA2-lib (not on disk)"},
             "gbp_per_s": block_total * args.steps / (ms_max / 1e3) / 1e9,
             "cells_per_s": cells_total * args.steps / (ms_max / 1e3),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"]},
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            "gpu_launches": launches_per_step * args.steps, "pairs_retried_per_step": retried,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                          "kernel": "aw_align_kernel", "kernel_ms": k_ms, "algorithmic_bytes_per_launch": algo,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "note": "compulsory HBM traffic of this path is tiny (SURVEY 8d): the kernel is bound by integer issue + memory latency, see profiles/"},
+                         "note": "compulsory HBM traffic of this path is tiny (SURVEY 8d): the kernel is bound by memory latency + integer issue, see profiles/"},
         }
-        if not args.no_cpu_baseline:
+        sample = cpu_sample_pairs(args.config, pairs, os.cpu_count() or 1)
+        if not args.no_cpu_baseline and sample:
             import oracle_lib as O
 
             cores = os.cpu_count() or 1
-            sample = pairs[: max(2, 8 * cores)]
-            r = O.run_pairs(ids, seqs, sample, O.params(*SCORES), use_mash=True, threads=cores)
+            r = O.run_pairs(ids, seqs, sample, O.params(*scores), use_mash=True, threads=cores)
             line["cpu_baseline"] = {"value": len(sample) / r["seconds"], "unit": "pairs/s", "cores": cores, "kind": "port",
                                     "sample": f"first {len(sample)} pairs of rank 0's shard, {cores} threads, {r['seconds']:.1f} s"}
             # parity of the same pairs, GPU vs CPU restatement, outside every timed region

@@ -39,7 +39,8 @@ typedef enum aw_status {
     AW_ECUDA = -3,         /* CUDA runtime error (see aw_last_error) */
     AW_ENOMEM = -4,        /* host or device allocation failed */
     AW_EUNSUPPORTED = -5,  /* e.g. match_score != 0, unknown orientation mode */
-    AW_EWORKSPACE = -6,    /* per-pair device workspace exhausted even after the retry ladder */
+    AW_EWORKSPACE = -6,    /* internal per-pair status: device workspace too small, the pair is re-run by the retry ladder
+                              (a pair that still fails after the ladder is delivered as AW_EALIGN + failure sentinel) */
     AW_ECALLBACK = -7,     /* the user callback returned non-zero; run cancelled */
     AW_EALIGN = -8         /* per-pair: alignment failed (mirrors AlignmentStatus != Completed) */
 } aw_status;
@@ -94,8 +95,10 @@ typedef struct aw_aligner aw_aligner;
 
 /* flags for aw_align_pairs / aw_batch_create */
 #define AW_FLAG_CIGAR_BYTES 1u  /* also materialise expanded cigar_bytes                    */
-#define AW_FLAG_ORDERED 2u      /* deliver results in pair order (default: completion order) */
+#define AW_FLAG_ORDERED 2u      /* accepted, no effect: per-result callbacks are always delivered in pair order within a call */
 #define AW_FLAG_NO_PAF 4u       /* skip PAF text (stats + cg only)                           */
+#define AW_FLAG_PAF_BLOCKS 8u   /* aw_align_stream: every PAF line is followed by '\n' in the device text arena and whole
+                                   batches are handed to the block callback (the CLI's writer, src/main.rs:347-367)   */
 
 /* ---- library / device ---- */
 int aw_abi_version(void);
@@ -106,8 +109,11 @@ int aw_device_count(void);                  /* 0 when no CUDA device is visible 
 /* ---- context: one per GPU (the path shards by pairs; no collective) ---- */
 int aw_create(int device, aw_ctx** out);
 void aw_destroy(aw_ctx* ctx);
-/* tuning knobs; key is one of "ctas_per_sm", "threads_per_cta", "max_wavefront_width", "hist_mb" */
+/* tuning knobs; key is one of "ctas_per_sm", "threads_per_cta", "max_wavefront_width", "hist_mb", "chunk_pairs",
+ * "ws16", "max_retry_attempts" (0 disables the retry ladder: pairs whose first-try workspace was too small fail) */
 int aw_set_option(aw_ctx* ctx, const char* key, int64_t value);
+/* returns every parked device / pinned buffer of the library's caching allocator to the driver */
+void aw_trim_cache(void);
 
 /* Copies the sequences (ASCII, any bytes) to the device, builds the reverse complements
  * (reverse_complement, src/alignment.rs:178-190), the 2-bit packing and validity flags.
@@ -123,6 +129,18 @@ int aw_set_orientation_params(aw_ctx* ctx, const aw_params* params);
 /* ---- the hot path, host-facing: align a pair list, stream results to a callback ---- */
 int aw_align_pairs(aw_ctx* ctx, const aw_params* params, int orientation_mode, const aw_pair* pairs,
                    uint64_t npairs, uint32_t flags, aw_result_cb cb, void* user);
+
+/* Streaming form of the same call (the parallel driver of src/iterator.rs:208-252 + the CLI's writer thread,
+ * src/main.rs:347-374): the library PULLS chunks of the pair list from `next` (returns the number of pairs and sets
+ * *pairs, valid until the following call; 0 ends the run) and keeps two batches in flight per context: while batch k+1
+ * runs on the GPU, batch k is copied back on a second stream and delivered.  Several contexts (GPUs) can pull from one
+ * shared source, which is how the host shards a pair list dynamically.  Delivery: `cb` per result (may be NULL), and/or
+ * -- with AW_FLAG_PAF_BLOCKS -- `block_cb` with newline-terminated PAF text (`n_lines` lines, completion order).
+ * A non-zero return of either callback cancels the run with AW_ECALLBACK. */
+typedef uint64_t (*aw_chunk_source)(void* user, const aw_pair** pairs);
+typedef int (*aw_paf_block_cb)(const char* text, uint64_t len, uint64_t n_lines, void* user);
+int aw_align_stream(aw_ctx* ctx, const aw_params* params, int orientation_mode, uint32_t flags, aw_chunk_source next,
+                    void* next_user, aw_result_cb cb, aw_paf_block_cb block_cb, void* user);
 
 /* ---- the hot path, device-resident (what bench.py times as `value`) ----
  * create: uploads the pair list and sizes the workspace; launch: enqueues every kernel of the
@@ -147,6 +165,9 @@ void aw_batch_destroy(aw_ctx* ctx, aw_batch* batch);
 
 /* ---- orientation only: out_is_reverse[i] in {0,1} for each pair (AW_ORIENT_MASH) ---- */
 int aw_orient_pairs(aw_ctx* ctx, const aw_pair* pairs, uint64_t npairs, uint8_t* out_is_reverse);
+/* scheduling aid (north_star: "partitioner balanced by predicted cost (length times divergence)"): out[i] = mash distance
+ * of pair i estimated from the stranded sketches of the strand determine_orientation_mash would pick, in [0,1] */
+int aw_estimate_divergence(aw_ctx* ctx, const aw_pair* pairs, uint64_t npairs, float* out);
 /* stranded (canonical=0; slot 2*i forward, 2*i+1 reverse-complement) or canonical (canonical=1;
  * one per sequence) bottom-`sketch_size` sketch of sequence `idx`; returns the entry count in
  * *out_n (<= sketch_size), entries ascending with duplicates kept */

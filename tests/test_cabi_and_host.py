@@ -206,3 +206,70 @@ def test_cli_surface_presets_filters_gz(tmp_path):
     with open(gz, "ab") as f:
         f.write(gzip.compress(text[30:].encode()))
     assert H.read_fasta(gz) == (ids, tot)
+
+
+def _c_type_to_rust(t):
+    """canonical Rust spelling of a C parameter / return type of include/allwave_cuda.h"""
+    t = re.sub(r"\s+", " ", t.strip())
+    t = re.sub(r"\s*\*\s*", "*", t)
+    table = {
+        "void": "()", "int": "c_int", "int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "uint64_t": "u64", "uint8_t": "u8", "float": "f32",
+        "const char*": "*const c_char", "char*": "*mut c_char", "void*": "*mut c_void", "const uint8_t*": "*const u8", "uint8_t*": "*mut u8",
+        "const uint64_t*": "*const u64", "uint64_t*": "*mut u64", "uint32_t*": "*mut u32", "float*": "*mut f32",
+        "const uint8_t*const*": "*const *const u8", "const char*const*": "*const *const c_char",
+        "aw_ctx*": "*mut aw_ctx", "const aw_ctx*": "*const aw_ctx", "aw_ctx**": "*mut *mut aw_ctx",
+        "aw_batch*": "*mut aw_batch", "aw_batch**": "*mut *mut aw_batch",
+        "aw_aligner*": "*mut aw_aligner", "const aw_aligner*": "*const aw_aligner", "aw_aligner**": "*mut *mut aw_aligner",
+        "const aw_params*": "*const aw_params", "const aw_pair*": "*const aw_pair",
+        "aw_result_cb": "aw_result_cb", "aw_chunk_source": "aw_chunk_source", "aw_paf_block_cb": "aw_paf_block_cb",
+    }
+    return table[t]
+
+
+def test_rust_sys_crate_matches_header():
+    """bindings/allwave-cuda-sys/src/lib.rs (source only: no Rust toolchain in this image) declares exactly the functions
+    of include/allwave_cuda.h with the same arity and the same pointer / integer widths, and the same struct layouts"""
+    hdr = open(os.path.join(ROOT, "include", "allwave_cuda.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    rs = open(os.path.join(ROOT, "bindings", "allwave-cuda-sys", "src", "lib.rs")).read()
+    rs = re.sub(r"//.*", "", rs)
+    cdecl = {}
+    for ret, name, args in re.findall(r"^\s*([A-Za-z_][\w \*]*?)\s*\b(aw_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.M | re.S):
+        if "typedef" in ret:
+            continue
+        params = []
+        for a in [x.strip() for x in args.replace("\n", " ").split(",")]:
+            if a in ("", "void"):
+                continue
+            is_array = bool(re.search(r"\[\d*\]$", a))
+            a = re.sub(r"\[\d*\]$", "", a)
+            m = re.match(r"(.*?)(\b[A-Za-z_]\w*)$", a)
+            ty = m.group(1).strip() if m and m.group(1).strip() else a
+            params.append(ty + "*" if is_array else ty)
+        cdecl[name] = (ret.strip(), params)
+    ext = re.search(r'extern "C" \{(.*?)\n\}', rs, flags=re.S).group(1)
+    rdecl = {}
+    for name, args, ret in re.findall(r"pub fn (aw_[a-z0-9_]+)\s*\((.*?)\)\s*(?:->\s*([^;]+?))?\s*;", ext, flags=re.S):
+        params = [re.sub(r"\s+", " ", a.split(":", 1)[1].strip()) for a in args.replace("\n", " ").split(",") if ":" in a]
+        rdecl[name] = ((ret or "()").strip(), params)
+    assert set(cdecl) == set(rdecl) == set(aw._cabi.EXPORTS), (set(cdecl) ^ set(rdecl), set(cdecl) ^ set(aw._cabi.EXPORTS))
+    for name, (cret, cparams) in cdecl.items():
+        rret, rparams = rdecl[name]
+        want = [_c_type_to_rust(p) for p in cparams]  # arrays in prototypes (uint64_t out[8]) decay to pointers
+        assert rparams == want, (name, rparams, want)
+        assert rret == _c_type_to_rust(cret), (name, rret, cret)
+    # struct fields, in order
+    for cname in ("aw_params", "aw_pair", "aw_result"):
+        cbody = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, flags=re.S).group(1)
+        cfields = []
+        for decl in [d.strip() for d in cbody.split(";") if d.strip()]:
+            m = re.match(r"(.*?)(\b\w+(?:\s*,\s*\w+)*)$", decl)
+            for f in [x.strip() for x in m.group(2).split(",")]:
+                cfields.append((f, _c_type_to_rust(m.group(1))))
+        rbody = re.search(r"pub struct %s \{(.*?)\}" % cname, rs, flags=re.S).group(1)
+        rfields = [(n, re.sub(r"\s+", " ", t.strip())) for n, t in re.findall(r"pub (\w+)\s*:\s*([^,]+),", rbody)]
+        assert rfields == cfields, (cname, rfields, cfields)
+    # status / flag constants
+    for cname, val in re.findall(r"\b(AW_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr) + re.findall(r"#define (AW_FLAG_[A-Z_]+) (\d+)u", hdr):
+        m = re.search(r"pub const %s: \w+ = (-?\d+);" % cname, rs)
+        assert m and int(m.group(1)) == int(val), cname
