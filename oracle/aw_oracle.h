@@ -71,6 +71,11 @@ int awo_wfa_align_unidirectional(const awo_params_t* params, const uint8_t* patt
 void awo_alignment_free(awo_alignment_t* a);
 /* if non-NULL, every breakpoint / base case is logged here (debug aid for the CUDA path) */
 void awo_set_trace_file(void* stdio_file);
+/* opt-in fast mode of the biWFA restatement for the CPU *baseline* legs (free lists, unchecked interior loop, 8-byte extend);
+ * results are identical to the plain path (tests/test_oracle.py::test_fast_mode_agrees) */
+void awo_set_fast(int on);
+int awo_get_fast(void);
+void awo_pool_release(void);
 
 /* penalty of a WFA2 op string under params (gap run L costs min(o1+L*e1, o2+L*e2)) */
 int64_t awo_cigar_penalty(const awo_params_t* params, const uint8_t* ops, size_t n);

@@ -58,6 +58,7 @@ static void* worker(void* arg) {
         work_add(&local, &r.work);
         awo_result_free(&r);
     }
+    awo_pool_release();
     pthread_mutex_lock(&c->mu);
     work_add(&c->out->work, &local);
     c->out->sum_block_len += block;

@@ -29,6 +29,7 @@ typedef struct {
     int null;   /* lo > hi */
     int alo;    /* off[k - alo] */
     int32_t* off;
+    size_t cap; /* allocated elements */
 } wf_t;
 
 typedef struct {
@@ -47,6 +48,9 @@ typedef struct {
     int tlen;
     int reverse;
     int comp_begin, comp_end;
+    /* fast mode: forward-readable copies for the reverse aligner (p[v] == rp[v]) */
+    uint8_t *rp, *rt;
+    size_t rp_cap, rt_cap;
     /* components, indexed by score (mod scope when modular) */
     wf_t** comp[5];
     int nslots;
@@ -55,7 +59,7 @@ typedef struct {
     awo_work_t* work;
 } aligner_t;
 
-static wf_t g_wf_null = {1, -1, 1, 0, NULL}; /* wavefront_null: lo=1, hi=-1 */
+static wf_t g_wf_null = {1, -1, 1, 0, NULL, 0}; /* wavefront_null: lo=1, hi=-1 */
 static FILE* g_trace = NULL;
 
 void awo_set_trace_file(void* f) { g_trace = (FILE*)f; }
@@ -63,18 +67,71 @@ void awo_set_trace_file(void* f) { g_trace = (FILE*)f; }
 static inline int pchar(const aligner_t* a, int v) { return a->reverse ? a->p[a->plen - 1 - v] : a->p[v]; }
 static inline int tchar(const aligner_t* a, int h) { return a->reverse ? a->t[a->tlen - 1 - h] : a->t[h]; }
 
+/*
+ * FAST MODE (awo_set_fast(1)) -- used by the CPU *baseline* legs of bench.py only; the checker keeps the simple path, and
+ * tests/test_oracle.py asserts that both give identical results.  It does what a WFA2-lib build does for speed and nothing
+ * else: (a) wavefronts come from a per-thread free list instead of malloc/free per score (WFA2's slab), (b) every wavefront is
+ * allocated with WF_PAD NULL cells either side so that the compute loop reads its inputs without range checks wherever all
+ * reads fall inside the padded allocations (wavefront_compute_init_ends), (c) the match extension compares 8 bytes at a time
+ * (XOR + ctz, wavefront_extend_matches_packed), the reverse aligner on reversed copies of the sequences.
+ */
+#define WF_PAD 64
+static int g_fast = 0;
+void awo_set_fast(int on) { g_fast = on ? 1 : 0; }
+int awo_get_fast(void) { return g_fast; }
+
+#define WF_POOL_MAX 512
+static __thread wf_t* t_pool[WF_POOL_MAX];
+static __thread int t_pool_n = 0;
+static __thread size_t t_pool_cap[WF_POOL_MAX];
+
+void awo_pool_release(void) { /* worker threads call this before they exit */
+    for (int i = 0; i < t_pool_n; ++i) {
+        free(t_pool[i]->off);
+        free(t_pool[i]);
+    }
+    t_pool_n = 0;
+}
+
 static wf_t* wf_new(int lo, int hi) {
-    wf_t* w = (wf_t*)malloc(sizeof(wf_t));
     int n = hi >= lo ? hi - lo + 1 : 0;
+    const int pad = g_fast ? WF_PAD : 0;
+    const size_t need = (size_t)(n > 0 ? n : 1) + 2 * (size_t)pad;
+    wf_t* w = NULL;
+    if (g_fast) {
+        for (int i = t_pool_n - 1; i >= 0 && i >= t_pool_n - 8; --i) /* recently freed wavefronts have the right size */
+            if (t_pool_cap[i] >= need) {
+                w = t_pool[i];
+                w->cap = t_pool_cap[i];
+                t_pool[i] = t_pool[t_pool_n - 1];
+                t_pool_cap[i] = t_pool_cap[t_pool_n - 1];
+                --t_pool_n;
+                break;
+            }
+    }
+    if (w == NULL) {
+        w = (wf_t*)malloc(sizeof(wf_t));
+        w->cap = g_fast ? need + need / 4 + 64 : need;
+        w->off = (int32_t*)malloc(sizeof(int32_t) * w->cap);
+    }
     w->lo = lo;
     w->hi = hi;
     w->null = lo > hi;
-    w->alo = lo;
-    w->off = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    w->alo = lo - pad;
+    if (pad) {
+        for (int i = 0; i < pad; ++i) w->off[i] = OFFSET_NULL;
+        for (size_t i = (size_t)pad + (size_t)(n > 0 ? n : 1); i < need; ++i) w->off[i] = OFFSET_NULL;
+    }
     return w;
 }
 static void wf_free(wf_t* w) {
     if (w && w != &g_wf_null) {
+        if (g_fast && t_pool_n < WF_POOL_MAX) {
+            t_pool[t_pool_n] = w;
+            t_pool_cap[t_pool_n] = w->cap;
+            ++t_pool_n;
+            return;
+        }
         free(w->off);
         free(w);
     }
@@ -116,6 +173,8 @@ static void aligner_init(aligner_t* a, const pen_t* pen, int modular, awo_work_t
 }
 static void aligner_destroy(aligner_t* a) {
     aligner_clear(a);
+    free(a->rp);
+    free(a->rt);
     for (int c = 0; c < 5; ++c) free(a->comp[c]);
 }
 static inline int slot_of(const aligner_t* a, int score) { return a->modular ? score % a->scope : score; }
@@ -153,15 +212,27 @@ static void aligner_start(aligner_t* a, const uint8_t* p, int plen, const uint8_
     a->num_null_steps = 0;
     a->status = ST_OK;
     a->end_score = -1;
+    if (g_fast && reverse) { /* wavefront_sequences_init keeps reversed copies too */
+        if ((size_t)plen + 8 > a->rp_cap) {
+            a->rp_cap = (size_t)plen + 8 + (size_t)plen / 4;
+            a->rp = (uint8_t*)realloc(a->rp, a->rp_cap);
+        }
+        if ((size_t)tlen + 8 > a->rt_cap) {
+            a->rt_cap = (size_t)tlen + 8 + (size_t)tlen / 4;
+            a->rt = (uint8_t*)realloc(a->rt, a->rt_cap);
+        }
+        for (int i = 0; i < plen; ++i) a->rp[i] = p[plen - 1 - i];
+        for (int i = 0; i < tlen; ++i) a->rt[i] = t[tlen - 1 - i];
+    }
     wf_t* w = wf_new(0, 0);
-    w->off[0] = 0;
+    w->off[0 - w->alo] = 0;
     wf_set(a, comp_begin, 0, w);
 }
 
 /* wavefront_compute_trim_ends */
 static void wf_trim(const aligner_t* a, wf_t* w) {
     int k;
-    const int lo = w->lo;
+    const int lo = w->lo, old_hi = w->hi;
     for (k = w->hi; k >= lo; --k) {
         int32_t off = w->off[k - w->alo];
         uint32_t h = (uint32_t)off, v = (uint32_t)(off - k);
@@ -176,6 +247,10 @@ static void wf_trim(const aligner_t* a, wf_t* w) {
     }
     w->lo = k;
     w->null = (w->lo > w->hi);
+    if (g_fast) { /* cells trimmed away must read as NULL without a range check */
+        for (k = lo; k < w->lo && k <= old_hi; ++k) w->off[k - w->alo] = OFFSET_NULL;
+        for (k = (w->hi >= lo ? w->hi + 1 : lo); k <= old_hi; ++k) w->off[k - w->alo] = OFFSET_NULL;
+    }
 }
 
 /* wavefront_compute_affine / wavefront_compute_affine2p (+ _idm kernels, limits_input,
@@ -220,17 +295,67 @@ static void wf_compute(aligner_t* a, int s) {
     wf_t* out_i2 = (two && (!m_o2->null || !i2_e->null)) ? wf_new(lo, hi) : NULL;
     wf_t* out_d2 = (two && (!m_o2->null || !d2_e->null)) ? wf_new(lo, hi) : NULL;
     const uint32_t tlen = (uint32_t)a->tlen, plen = (uint32_t)a->plen;
+    int32_t* const om = out_m->off - out_m->alo;
+    int32_t* const oi1 = out_i1 ? out_i1->off - out_i1->alo : NULL;
+    int32_t* const od1 = out_d1 ? out_d1->off - out_d1->alo : NULL;
+    int32_t* const oi2 = out_i2 ? out_i2->off - out_i2->alo : NULL;
+    int32_t* const od2 = out_d2 ? out_d2->off - out_d2->alo : NULL;
+    /* fast mode: [f_lo, f_hi] = diagonals whose nine reads all fall inside the (NULL-padded) allocations of non-null inputs */
+    int f_lo = 1, f_hi = 0;
+    if (g_fast && !m_x->null && !m_o1->null && !i1_e->null && !d1_e->null && out_i1 && out_d1 &&
+        (!two || (!m_o2->null && !i2_e->null && !d2_e->null && out_i2 && out_d2))) {
+        f_lo = lo;
+        f_hi = hi;
+        const wf_t* ins[7] = {m_x, m_o1, i1_e, d1_e, m_o2, i2_e, d2_e};
+        for (int i = 0; i < (two ? 7 : 4); ++i) {
+            f_lo = MAXI(f_lo, ins[i]->lo - WF_PAD + 1);
+            f_hi = MINI(f_hi, ins[i]->hi + WF_PAD - 1);
+        }
+    }
     for (int k = lo; k <= hi; ++k) {
+        if (k == f_lo && f_lo <= f_hi) {
+            const int32_t* pmx = m_x->off - m_x->alo;
+            const int32_t* pmo1 = m_o1->off - m_o1->alo;
+            const int32_t* pi1 = i1_e->off - i1_e->alo;
+            const int32_t* pd1 = d1_e->off - d1_e->alo;
+            if (two) {
+                const int32_t* pmo2 = m_o2->off - m_o2->alo;
+                const int32_t* pi2 = i2_e->off - i2_e->alo;
+                const int32_t* pd2 = d2_e->off - d2_e->alo;
+                for (int q = f_lo; q <= f_hi; ++q) {
+                    const int32_t ins1 = MAXI(pmo1[q - 1], pi1[q - 1]) + 1, del1 = MAXI(pmo1[q + 1], pd1[q + 1]);
+                    const int32_t ins2 = MAXI(pmo2[q - 1], pi2[q - 1]) + 1, del2 = MAXI(pmo2[q + 1], pd2[q + 1]);
+                    oi1[q] = ins1;
+                    od1[q] = del1;
+                    oi2[q] = ins2;
+                    od2[q] = del2;
+                    int32_t mx = MAXI(MAXI(del1, del2), MAXI(pmx[q] + 1, MAXI(ins1, ins2)));
+                    if ((uint32_t)mx > tlen || (uint32_t)(mx - q) > plen) mx = OFFSET_NULL;
+                    om[q] = mx;
+                }
+            } else {
+                for (int q = f_lo; q <= f_hi; ++q) {
+                    const int32_t ins1 = MAXI(pmo1[q - 1], pi1[q - 1]) + 1, del1 = MAXI(pmo1[q + 1], pd1[q + 1]);
+                    oi1[q] = ins1;
+                    od1[q] = del1;
+                    int32_t mx = MAXI(del1, MAXI(pmx[q] + 1, ins1));
+                    if ((uint32_t)mx > tlen || (uint32_t)(mx - q) > plen) mx = OFFSET_NULL;
+                    om[q] = mx;
+                }
+            }
+            k = f_hi;
+            continue;
+        }
         int32_t ins1 = MAXI(wf_at(m_o1, k - 1), wf_at(i1_e, k - 1)) + 1;
         int32_t del1 = MAXI(wf_at(m_o1, k + 1), wf_at(d1_e, k + 1));
         int32_t ins = ins1, del = del1;
-        if (out_i1) out_i1->off[k - lo] = ins1;
-        if (out_d1) out_d1->off[k - lo] = del1;
+        if (out_i1) oi1[k] = ins1;
+        if (out_d1) od1[k] = del1;
         if (two) {
             int32_t ins2 = MAXI(wf_at(m_o2, k - 1), wf_at(i2_e, k - 1)) + 1;
             int32_t del2 = MAXI(wf_at(m_o2, k + 1), wf_at(d2_e, k + 1));
-            if (out_i2) out_i2->off[k - lo] = ins2;
-            if (out_d2) out_d2->off[k - lo] = del2;
+            if (out_i2) oi2[k] = ins2;
+            if (out_d2) od2[k] = del2;
             ins = MAXI(ins, ins2);
             del = MAXI(del, del2);
         }
@@ -239,7 +364,7 @@ static void wf_compute(aligner_t* a, int s) {
         uint32_t h = (uint32_t)mx, v = (uint32_t)(mx - k);
         if (h > tlen) mx = OFFSET_NULL;
         if (v > plen) mx = OFFSET_NULL;
-        out_m->off[k - lo] = mx;
+        om[k] = mx;
     }
     a->work->cells += (uint64_t)(hi - lo + 1) * (two ? 5 : 3);
     if ((uint64_t)(hi - lo + 1) > a->work->max_width) a->work->max_width = (uint64_t)(hi - lo + 1);
@@ -292,6 +417,29 @@ static int wf_extend(aligner_t* a, int score, int* max_ak) {
         int32_t off = mwf->off[k - mwf->alo];
         if (off == OFFSET_NULL) continue;
         int v = off - k, h = off;
+        if (g_fast) { /* 8 bytes per step on forward-readable sequences (wavefront_extend_matches_packed) */
+            const uint8_t* ps = a->reverse ? a->rp : a->p;
+            const uint8_t* ts = a->reverse ? a->rt : a->t;
+            while (v + 8 <= a->plen && h + 8 <= a->tlen) {
+                uint64_t x, y;
+                memcpy(&x, ps + v, 8);
+                memcpy(&y, ts + h, 8);
+                const uint64_t d = x ^ y;
+                if (d) {
+                    const int n = __builtin_ctzll(d) >> 3;
+                    v += n;
+                    h += n;
+                    goto extended;
+                }
+                v += 8;
+                h += 8;
+            }
+            while (v < a->plen && h < a->tlen && ps[v] == ts[h]) {
+                ++v;
+                ++h;
+            }
+        extended:;
+        } else
         while (v < a->plen && h < a->tlen && pchar(a, v) == tchar(a, h)) {
             ++v;
             ++h;

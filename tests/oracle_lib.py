@@ -308,8 +308,19 @@ def build_knn_graph(matrix, k, farthest):
     return out
 
 
-def run_pairs(ids, seqs, pairs, p, use_mash=True, threads=1):
+def set_fast(on):
+    """opt-in fast mode of the biWFA restatement (free lists, unchecked interior loop, 8-byte extend): for CPU baseline legs"""
+    lib().awo_set_fast(1 if on else 0)
+
+
+def run_pairs(ids, seqs, pairs, p, use_mash=True, threads=1, fast=False):
     """whole-job CPU driver -> dict(paf=[...], scores=[...], seconds=..., sum_block_len=..., work={...})"""
+    if fast:
+        set_fast(True)
+        try:
+            return run_pairs(ids, seqs, pairs, p, use_mash, threads, fast=False)
+        finally:
+            set_fast(False)
     n = len(ids)
     idarr, seqarr, lens = _seq_arrays(ids, seqs)
     flat = (C.c_uint64 * max(1, 2 * len(pairs)))()

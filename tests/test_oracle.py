@@ -217,3 +217,19 @@ def test_run_pairs_threads_agree(oracle):
     a = oracle.run_pairs(ids, seqs, pairs, oracle.params(), threads=1)
     b = oracle.run_pairs(ids, seqs, pairs, oracle.params(), threads=4)
     assert a["paf"] == b["paf"] and a["scores"] == b["scores"] and a["sum_block_len"] == b["sum_block_len"]
+
+
+def test_fast_mode_agrees(oracle):
+    """the opt-in fast mode of the restatement (bench baseline legs) gives byte-identical PAF and scores"""
+    O = oracle
+
+    rnd = random.Random(11)
+    for (n, length, d, pen) in [(10, 600, 0.05, (0, 5, 8, 2, 24, 1)), (8, 300, 0.2, (0, 1, 1, 1, None, None)), (6, 2500, 0.03, (0, 4, 6, 2, None, None)),
+                                (12, 90, 0.1, (0, 5, 8, 2, 24, 1)), (4, 7000, 0.05, (0, 5, 8, 2, 24, 1)), (6, 1000, 0.02, (0, 4, 12, 1, 6, 3))]:
+        ids, seqs, _ = synth.generate(rnd.randrange(1 << 30), n, length, d, rc_prob=0.3)
+        seqs[0] = seqs[1][: length // 2]  # a long end gap
+        pairs = [(i, j) for i in range(n) for j in range(n) if i != j]
+        p = O.params(*pen)
+        a = O.run_pairs(ids, seqs, pairs, p, use_mash=True, threads=4)
+        b = O.run_pairs(ids, seqs, pairs, p, use_mash=True, threads=4, fast=True)
+        assert a["paf"] == b["paf"] and a["scores"] == b["scores"] and a["work"]["cells"] == b["work"]["cells"]
