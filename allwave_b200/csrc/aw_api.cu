@@ -181,6 +181,8 @@ struct aw_ctx {
     int64_t hist_mb = 16;      // base-case history arena per CTA (first attempt)
     int64_t chunk_pairs = 65536;
     int ws16 = 1;              // 1 = int16 wavefront storage when every offset fits
+    int64_t cluster_min_len = 200000;  // pairs at least this long (2-bit sequences, int32 rows) run one pair per thread-block cluster; 0 = never
+    int64_t solo_len = 65536;          // ... and inside them sub-problems with plen + tlen below this are left to CTA 0 of the cluster
     int max_retry = 3;         // rungs of the retry ladder (0: a pair whose first-try workspace was too small fails)
     // streams: `stream` runs the kernels (they serialise: every launch fills the GPU), `up_stream` uploads the next batch's
     // pair list, `copy_stream` brings the previous batch's results back while the next kernel runs
@@ -199,8 +201,13 @@ struct aw_ctx {
     SketchSet stranded;
     bool have_stranded = false;
     std::map<std::pair<int, uint32_t>, SketchSet*> canonical;
-    // grow-only per-launch workspace (one launch in flight per context)
-    DevBuf ws_main, ws_hist_meta, ws_runs, ws_blk, ws_seq2;
+    // grow-only per-launch workspace.  Two sets: the streaming driver alternates its two batches between them and between
+    // two kernel streams, so that the first CTAs of batch k+1 start on the SMs that the tail of batch k leaves idle
+    struct Workspace {
+        DevBuf ws_main, ws_hist_meta, ws_runs, ws_blk, ws_seq2;
+        size_t bytes() const { return ws_main.cap + ws_hist_meta.cap + ws_runs.cap + ws_blk.cap + ws_seq2.cap; }
+    } wsp[2];
+    cudaStream_t stream2 = nullptr;  // kernel stream of workspace set 1 (set 0 runs on `stream`)
 };
 
 struct aw_batch {
@@ -226,6 +233,8 @@ struct aw_batch {
     uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     uint64_t cyc[6] = {0, 0, 0, 0, 0, 0};
     bool launched = false;
+    int slot = 0;                              // workspace set / kernel stream of the context this batch runs on
+    cudaStream_t last_stream = nullptr;        // stream of the last launch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // around the alignment kernel of the last launch
     cudaEvent_t ev_done = nullptr;             // after the last kernel of the launch (what fetch waits for)
 };
@@ -283,6 +292,7 @@ extern "C" int aw_create(int device, aw_ctx** out) {
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->up_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_sketch, cudaEventDisableTiming);
@@ -317,12 +327,15 @@ extern "C" void aw_destroy(aw_ctx* c) {
     c->d_packed.release();
     c->d_ids.release();
     c->d_id_off.release();
-    c->ws_main.release();
-    c->ws_hist_meta.release();
-    c->ws_blk.release();
-    c->ws_seq2.release();
-    c->ws_runs.release();
+    for (auto& w : c->wsp) {
+        w.ws_main.release();
+        w.ws_hist_meta.release();
+        w.ws_blk.release();
+        w.ws_seq2.release();
+        w.ws_runs.release();
+    }
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->up_stream) cudaStreamDestroy(c->up_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_sketch) cudaEventDestroy(c->ev_sketch);
@@ -347,13 +360,19 @@ extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
     std::string k(key);
     if (k == "ctas_per_sm") c->ctas_per_sm = (int)value;
     else if (k == "threads_per_cta") {
+#ifdef AW_NT_EXPERIMENT
+        if (value != 0 && value != 32 && value != 128 && value != 256 && value != AW_NT_EXPERIMENT) return AW_EINVAL;
+#else
         if (value != 0 && value != 32 && value != 128 && value != 256) return AW_EINVAL;
+#endif
         c->threads_per_cta = (int)value;
     } else if (k == "max_wavefront_width") c->max_w = value;
     else if (k == "hist_mb") c->hist_mb = value;
     else if (k == "chunk_pairs") c->chunk_pairs = value > 0 ? value : 65536;
     else if (k == "band_engine") (void)value;  // accepted for compatibility: the experimental band engine of the first kernels is gone
     else if (k == "ws16") c->ws16 = value ? 1 : 0;
+    else if (k == "cluster_min_len") c->cluster_min_len = value;
+    else if (k == "solo_len") c->solo_len = std::max<int64_t>(0, value);
     else if (k == "max_retry_attempts") c->max_retry = (int)std::max<int64_t>(0, std::min<int64_t>(3, value));
     else return AW_EINVAL;
     return AW_OK;
@@ -376,6 +395,7 @@ extern "C" int aw_load_sequences(aw_ctx* c, uint32_t n, const uint8_t* const* se
     if (!c || (n && (!seqs || !lens))) return AW_EINVAL;
     AW_CUDA_CHECK(cudaSetDevice(c->device));
     AW_CUDA_CHECK(cudaStreamSynchronize(c->stream));  // nothing may still read the store that is about to be replaced
+    AW_CUDA_CHECK(cudaStreamSynchronize(c->stream2));
     free_sketches(c);
     c->n = n;
     c->lens.assign(lens, lens + n);
@@ -661,7 +681,7 @@ extern "C" void aw_batch_destroy(aw_ctx* c, aw_batch* b) {
     if (c) cudaSetDevice(c->device);
     if (b->launched) {  // never park buffers a kernel still uses
         if (b->ev_done) cudaEventSynchronize(b->ev_done);
-        if (c) cudaStreamSynchronize(c->stream);
+        if (b->last_stream) cudaStreamSynchronize(b->last_stream);
     }
     b->d_pairs.release();
     b->d_isrev.release();
@@ -786,8 +806,12 @@ extern "C" int aw_batch_create(aw_ctx* c, const aw_params* params, int orientati
 
 namespace {
 
+// Mb-scale pairs: CTAs per pair (thread-block cluster; 8 is the largest portable cluster size)
+#define AW_CLUSTER_SIZE 8
+
 struct LaunchCfg {
     int nt, grid;
+    int cluster;  // CTAs per pair: 1, or the cluster size of the Mb-scale kernels (grid = clusters * cluster)
     int W;
     unsigned long long ws_ints, hist_ints, runs_cap;
     bool ws16;
@@ -796,9 +820,9 @@ struct LaunchCfg {
     unsigned long long seq2_cap;
 };
 
-template <int NT, int BITS, bool TWO, class WS>
+template <int NT, int BITS, bool TWO, class WS, int CL = 1>
 cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStream_t st) {
-    auto kern = awk::aw_align_kernel<NT, BITS, TWO, WS>;
+    auto kern = awk::aw_align_kernel<NT, BITS, TWO, WS, CL>;
     // static + dynamic shared memory together decide whether the opt-in is needed (the kernels carry up to 28 KB of static
     // shared memory); query the static part once per instantiation
     static size_t static_smem = ~(size_t)0;
@@ -819,13 +843,41 @@ cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStrea
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
+    if (CL > 1) {  // one pair per thread-block cluster
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)grid);
+        lc.blockDim = dim3(NT);
+        lc.dynamicSmemBytes = smem;
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        // the CTAs are persistent: launching more clusters than can be resident at once buys nothing
+        int max_clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&max_clusters, kern, &lc) == cudaSuccess && max_clusters > 0 && grid / CL > max_clusters)
+            lc.gridDim = dim3((unsigned)(max_clusters * CL));
+        else
+            cudaGetLastError();
+        return cudaLaunchKernelEx(&lc, kern, P);
+    }
     kern<<<grid, NT, smem, st>>>(P);
     return cudaGetLastError();
 }
 
-cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bool ws16, int grid, cudaStream_t st) {
+cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bool ws16, int grid, cudaStream_t st, int cluster = 1) {
     const int scope = P.pen.scope;
     size_t smem = sizeof(awk::SlotMeta) * 2 * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt + sizeof(int) * (10 * scope + 4);
+    if (cluster == AW_CLUSTER_SIZE && nt == 256 && bits == 2 && !ws16) {
+        if (two) return launch_align<256, 2, true, int, AW_CLUSTER_SIZE>(P, grid, smem, st);
+#ifndef AW_FAST_BUILD
+        return launch_align<256, 2, false, int, AW_CLUSTER_SIZE>(P, grid, smem, st);
+#endif
+    }
+    if (cluster != 1) return cudaErrorInvalidConfiguration;
 #define AW_CASE(NT_, BITS_, TWO_, WS_, W16_) \
     if (nt == NT_ && bits == BITS_ && two == TWO_ && ws16 == W16_) return launch_align<NT_, BITS_, TWO_, WS_>(P, grid, smem, st);
 #ifndef AW_FAST_BUILD  // dev builds (-DAW_FAST_BUILD) keep only the two-piece 2-bit int16 kernels
@@ -845,6 +897,9 @@ cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bo
 #endif
     AW_CASE(256, 2, true, short, true)
     AW_CASE(128, 2, true, short, true)
+#ifdef AW_NT_EXPERIMENT  // tuning builds: another CTA size for the int16 two-piece kernel (set_option threads_per_cta)
+    AW_CASE(AW_NT_EXPERIMENT, 2, true, short, true)
+#endif
     AW_CASE(128, 2, true, int, false)
 #undef AW_CASE
     return cudaErrorInvalidValue;
@@ -852,7 +907,9 @@ cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bo
 
 // sizes the per-CTA workspace for one launch; attempt 0 is the fast first try, later attempts
 // remove the wavefront-width cap and grow the history arena (retry ladder)
-int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, uint64_t max_t, int attempt, LaunchCfg* cfg) {
+int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, uint64_t max_t, int attempt, LaunchCfg* cfg, int slot = 0) {
+    aw_ctx::Workspace& w = c->wsp[slot];
+    cudaStream_t kst = slot ? c->stream2 : c->stream;
     const int ncomp = pen.two_piece ? 5 : 3;
     const uint64_t maxlen = std::max(max_p, max_t);
     // int16 storage: every offset (incl. out-of-bounds I/D drift, <= 2*tlen+plen) must stay below 32000
@@ -862,6 +919,9 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     // measured best on C2); everything else: 256 threads
     // (20 kb pairs, int32 rows: 571 pairs/s with 128 threads vs 501 with 256); Mb-scale pairs keep 256 threads per pair
     int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : ((c->all_clean && (fits16 || maxlen <= 50000)) ? 128 : 256));
+    // Mb-scale pairs: one pair per cluster of AW_CLUSTER_SIZE 256-thread CTAs (few pairs in flight, each on 2048 threads)
+    const bool use_cluster = c->cluster_min_len > 0 && c->all_clean && !fits16 && (int64_t)maxlen >= c->cluster_min_len && !c->threads_per_cta;
+    if (use_cluster) nt = 256;
     int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : AW_CTAS_PER_SM(nt));
     uint64_t full_w = (max_p + max_t + 3 + 16 + 15) & ~15ull;  // rows are 16-element aligned (vectorised int16 loop)
     uint64_t W = full_w;
@@ -882,8 +942,10 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
         std::lock_guard<std::mutex> g(g_cache.mu);
         parked = g_cache.parked_dev[c->device >= 0 && c->device < 64 ? c->device : 0];
     }
-    const uint64_t budget = (uint64_t)((double)(free_b + parked + c->ws_main.cap + c->ws_hist_meta.cap + c->ws_runs.cap + c->ws_blk.cap + c->ws_seq2.cap) * 0.85);
-    const uint64_t want_grid = std::min<uint64_t>((uint64_t)c->sm_count * per_sm, std::max<uint64_t>(1, npairs));
+    const uint64_t budget = (uint64_t)((double)(free_b + parked + w.bytes()) * 0.85);
+    // workspace slots = pairs in flight: one per CTA, or one per cluster
+    const uint64_t want_grid = std::min<uint64_t>(use_cluster ? std::max<uint64_t>(1, (uint64_t)c->sm_count * per_sm / AW_CLUSTER_SIZE) : (uint64_t)c->sm_count * per_sm,
+                                                  std::max<uint64_t>(1, npairs));
     if (attempt == 0) {
         // first try: as many diagonals per wavefront as let every resident CTA have its own workspace (a wavefront
         // is at most 2*score+1 wide, far below plen+tlen for similar sequences); pairs that need more report
@@ -913,7 +975,8 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
         return AW_ENOMEM;
     }
     cfg->nt = nt;
-    cfg->grid = (int)grid;
+    cfg->cluster = use_cluster ? AW_CLUSTER_SIZE : 1;
+    cfg->grid = (int)grid * cfg->cluster;
     cfg->W = (int)std::min<uint64_t>(W, 0x7ffffff0ull);
     cfg->ws_ints = ws_ints;
     cfg->hist_ints = hist_ints * epi;  // capacity in workspace elements
@@ -925,14 +988,14 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     cfg->seq2_cap = (!ws16 && nt >= 64 && c->all_clean) ? 2 * ((max_p / 16 + 2) + (max_t / 16 + 2)) : 0;
     int rc;
     // growing a workspace re-allocates it: a kernel of an earlier batch that is still running must not lose its buffers
-    if (grid * ws_ints * 4 > c->ws_main.cap || grid * 2ull * (pen.scope + 1) * (uint64_t)cfg->blk_cap * 2 * 4 > c->ws_blk.cap ||
-        grid * cfg->seq2_cap * 8 + 16 > c->ws_seq2.cap || grid * (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 > c->ws_hist_meta.cap ||
-        grid * runs_cap * 8 > c->ws_runs.cap)
-        if (cudaStreamSynchronize(c->stream) != cudaSuccess) return AW_ECUDA;
-    if ((rc = c->ws_main.ensure(grid * ws_ints * 4)) ||
-        (rc = c->ws_blk.ensure(grid * 2ull * (pen.scope + 1) * (uint64_t)cfg->blk_cap * 2 * 4)) ||
-        (rc = c->ws_seq2.ensure(grid * cfg->seq2_cap * 8 + 16)) ||
-        (rc = c->ws_hist_meta.ensure(grid * (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4)) || (rc = c->ws_runs.ensure(grid * runs_cap * 8)))
+    if (grid * ws_ints * 4 > w.ws_main.cap || grid * 2ull * (pen.scope + 1) * (uint64_t)cfg->blk_cap * 2 * 4 > w.ws_blk.cap ||
+        grid * cfg->seq2_cap * 8 + 16 > w.ws_seq2.cap || grid * (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4 > w.ws_hist_meta.cap ||
+        grid * runs_cap * 8 > w.ws_runs.cap)
+        if (cudaStreamSynchronize(kst) != cudaSuccess) return AW_ECUDA;
+    if ((rc = w.ws_main.ensure(grid * ws_ints * 4)) ||
+        (rc = w.ws_blk.ensure(grid * 2ull * (pen.scope + 1) * (uint64_t)cfg->blk_cap * 2 * 4)) ||
+        (rc = w.ws_seq2.ensure(grid * cfg->seq2_cap * 8 + 16)) ||
+        (rc = w.ws_hist_meta.ensure(grid * (uint64_t)hist_max_scores * awk::HIST_META_INTS * 4)) || (rc = w.ws_runs.ensure(grid * runs_cap * 8)))
         return rc;
     return AW_OK;
 }
@@ -948,18 +1011,20 @@ void fill_params(aw_ctx* c, aw_batch* b, const AwPen& pen, const LaunchCfg& cfg,
     P->is_reverse = b->d_isrev.as<uint8_t>();
     P->pen = pen;
     P->flags = b->flags;
-    P->ws = c->ws_main.as<int>();
+    const aw_ctx::Workspace& w = c->wsp[b->slot];
+    P->ws = w.ws_main.as<int>();
     P->ws_ints_per_cta = cfg.ws_ints;
     P->W = cfg.W;
     P->hist_ints = (int)std::min<unsigned long long>(cfg.hist_ints, 0x7fffffffull);
-    P->ws_hist_meta = c->ws_hist_meta.as<int>();
-    P->ws_blk = c->ws_blk.as<int>();
+    P->ws_hist_meta = w.ws_hist_meta.as<int>();
+    P->ws_blk = w.ws_blk.as<int>();
     P->blk_cap = cfg.blk_cap;
-    P->ws_seq2 = c->ws_seq2.as<uint2>();
+    P->ws_seq2 = w.ws_seq2.as<uint2>();
     P->seq2_cap = cfg.seq2_cap;
     P->hist_max_scores = cfg.hist_max_scores;
-    P->ws_runs = c->ws_runs.as<uint32_t>();
+    P->ws_runs = w.ws_runs.as<uint32_t>();
     P->runs_cap = cfg.runs_cap;
+    P->solo_len = (int)std::min<int64_t>(c->solo_len, 0x7fffffff);
 }
 
 }  // namespace
@@ -967,7 +1032,8 @@ void fill_params(aw_ctx* c, aw_batch* b, const AwPen& pen, const LaunchCfg& cfg,
 extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
     if (!c || !b) return AW_EINVAL;
     AW_CUDA_CHECK(cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = stream ? (cudaStream_t)stream : (b->slot ? c->stream2 : c->stream);
+    b->last_stream = st;
     memset(b->stats, 0, sizeof(b->stats));
     memset(b->cyc, 0, sizeof(b->cyc));
     b->r_out.clear();
@@ -985,13 +1051,13 @@ extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
         ++b->stats[0];
     }
     LaunchCfg cfg;
-    if ((rc = plan_launch(c, b->pen, b->npairs, b->max_p, b->max_t, 0, &cfg))) return rc;
+    if ((rc = plan_launch(c, b->pen, b->npairs, b->max_p, b->max_t, 0, &cfg, b->slot))) return rc;
     AW_CUDA_CHECK(cudaMemsetAsync(b->d_ctl.p, 0, 64, st));
     if (b->orient == AW_ORIENT_WFA) {
         // determine_orientation_wfa: two full alignments with the orientation penalties, forward and
         // reverse-complemented query, statistics only; then pick the strand with fewer X+I+D columns
         LaunchCfg cfo;
-        if ((rc = plan_launch(c, b->pen_orient, b->npairs, b->max_p, b->max_t, 0, &cfo))) return rc;  // never larger than the main plan
+        if ((rc = plan_launch(c, b->pen_orient, b->npairs, b->max_p, b->max_t, 0, &cfo, b->slot))) return rc;  // never larger than the main plan
         const size_t np1 = (size_t)std::max<uint64_t>(1, b->npairs);
         for (int strand = 0; strand < 2; ++strand) {
             awk::KParams Q;
@@ -1008,7 +1074,7 @@ extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
             Q.bytes = b->d_bytes.as<uint8_t>();
             Q.bytes_cursor = b->d_ctl.as<unsigned long long>() + 6;
             Q.bytes_cap = b->bytes_cap;
-            cudaError_t eo = dispatch_align(Q, cfo.nt, c->all_clean ? 2 : 8, b->pen_orient.two_piece != 0, cfo.ws16, cfo.grid, st);
+            cudaError_t eo = dispatch_align(Q, cfo.nt, c->all_clean ? 2 : 8, b->pen_orient.two_piece != 0, cfo.ws16, cfo.grid, st, cfo.cluster);
             if (eo != cudaSuccess) {
                 aw_set_error("orientation kernel launch: %s", cudaGetErrorString(eo));
                 return AW_ECUDA;
@@ -1037,7 +1103,7 @@ extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
         AW_CUDA_CHECK(cudaEventCreateWithFlags(&b->ev_done, cudaEventDisableTiming));
     }
     AW_CUDA_CHECK(cudaEventRecord(b->ev0, st));
-    cudaError_t e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.ws16, cfg.grid, st);
+    cudaError_t e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.ws16, cfg.grid, st, cfg.cluster);
     if (e != cudaSuccess) {
         aw_set_error("align kernel launch (nt=%d grid=%d): %s", cfg.nt, cfg.grid, cudaGetErrorString(e));
         return AW_ECUDA;
@@ -1059,6 +1125,7 @@ extern "C" int aw_batch_launch(aw_ctx* c, aw_batch* b, void* stream) {
 // passes go through the same ladder as the alignment itself, then the strand is picked like determine_orientation_wfa
 // (src/alignment.rs:157-175: a pass that still fails after the ladder counts as usize::MAX)
 static int retry_orientation(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
+    cudaStream_t kst = b->slot ? c->stream2 : c->stream;
     std::vector<uint32_t> todo;
     for (uint64_t i = 0; i < b->npairs; ++i)
         if (h_out[i].status == AW_EWORKSPACE && h_out[i].is_reverse > 1) todo.push_back((uint32_t)i);
@@ -1075,7 +1142,7 @@ static int retry_orientation(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
             max_t = std::max(max_t, c->lens[b->h_pairs[i].target_idx]);
         }
         LaunchCfg cfo;
-        int rc = plan_launch(c, b->pen_orient, todo.size(), max_p, max_t, attempt, &cfo);
+        int rc = plan_launch(c, b->pen_orient, todo.size(), max_p, max_t, attempt, &cfo, b->slot);
         if (rc) return rc;
         DevBuf d_order, d_ctl;
         if ((rc = d_order.ensure(4 * todo.size())) || (rc = d_ctl.ensure(64))) return rc;
@@ -1096,10 +1163,10 @@ static int retry_orientation(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
             Q.bytes = b->d_bytes.as<uint8_t>();
             Q.bytes_cursor = d_ctl.as<unsigned long long>() + 6;
             Q.bytes_cap = b->bytes_cap;
-            e = dispatch_align(Q, cfo.nt, c->all_clean ? 2 : 8, b->pen_orient.two_piece != 0, cfo.ws16, cfo.grid, c->stream);
+            e = dispatch_align(Q, cfo.nt, c->all_clean ? 2 : 8, b->pen_orient.two_piece != 0, cfo.ws16, cfo.grid, kst, cfo.cluster);
             ++b->stats[0];
         }
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(kst);
         if (e == cudaSuccess) e = cudaMemcpy(of.data(), b->d_out_f.p, sizeof(AwPairOut) * b->npairs, cudaMemcpyDeviceToHost);
         if (e == cudaSuccess) e = cudaMemcpy(orv.data(), b->d_out_r.p, sizeof(AwPairOut) * b->npairs, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) {
@@ -1141,9 +1208,10 @@ static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
         if (h_out[i].status == AW_EWORKSPACE) failed.push_back((uint32_t)i);
     if (failed.empty()) return AW_OK;
     b->stats[1] = failed.size();
-    // a later batch of the same context may already be running with the current workspace: let it finish before the
+    // a later batch may already be queued on this batch's kernel stream with the current workspace: let it finish before the
     // workspace is re-planned (and possibly re-allocated) for the retry
-    AW_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    cudaStream_t kst = b->slot ? c->stream2 : c->stream;
+    AW_CUDA_CHECK(cudaStreamSynchronize(kst));
     if (b->orient == AW_ORIENT_WFA) {
         int rc = retry_orientation(c, b, h_out);
         if (rc) return rc;
@@ -1171,7 +1239,7 @@ static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
             idlen_max = std::max(idlen_max, c->ids[b->h_pairs[i].query_idx].size() + c->ids[b->h_pairs[i].target_idx].size());
         }
         LaunchCfg cfg;
-        int rc = plan_launch(c, b->pen, failed.size(), max_p, max_t, attempt, &cfg);
+        int rc = plan_launch(c, b->pen, failed.size(), max_p, max_t, attempt, &cfg, b->slot);
         if (rc) return rc;
         const uint64_t text_cap = 12 * sum_len + (256 + idlen_max) * failed.size() + 1024;
         const uint64_t bytes_cap = (b->flags & AW_FLAG_CIGAR_BYTES) ? sum_len + 16 : 16;
@@ -1193,9 +1261,9 @@ static int retry_failed(aw_ctx* c, aw_batch* b, const AwPairOut* h_out) {
         P.bytes = d_bytes.as<uint8_t>();
         P.bytes_cursor = d_ctl.as<unsigned long long>() + 1;
         P.bytes_cap = bytes_cap;
-        if (e == cudaSuccess) e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.ws16, cfg.grid, c->stream);
+        if (e == cudaSuccess) e = dispatch_align(P, cfg.nt, c->all_clean ? 2 : 8, b->pen.two_piece != 0, cfg.ws16, cfg.grid, kst, cfg.cluster);
         ++b->stats[0];
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(kst);
         std::vector<AwPairOut> outs(b->npairs);
         unsigned long long ctl[3] = {0, 0, 0};
         if (e == cudaSuccess) e = cudaMemcpy(outs.data(), d_out.p, sizeof(AwPairOut) * b->npairs, cudaMemcpyDeviceToHost);
@@ -1377,13 +1445,21 @@ extern "C" int aw_align_stream(aw_ctx* c, const aw_params* params, int orientati
     aw_batch* slot[2] = {new aw_batch(), new aw_batch()};
     bool busy[2] = {false, false};
     int rc = AW_OK;
+    // second workspace set + kernel stream for the odd batches, unless one set already takes a large share of the device
+    // (Mb-scale pairs): then both batches share set 0 and simply queue behind each other
+    bool two_sets = true;
     auto feed = [&](int s) -> int {  // pulls the next chunk into slot s and queues its kernels; busy[s] says whether there was one
         const aw_pair* pairs = nullptr;
         const uint64_t n = next(next_user, &pairs);
         if (n == 0) return AW_OK;
         if (!pairs || n > 0xfffffff0ull) return AW_EINVAL;
         int r = batch_init(c, slot[s], params, orientation_mode, pairs, n, flags);
+        slot[s]->slot = (two_sets && s == 1) ? 1 : 0;
         if (r == AW_OK) r = aw_batch_launch(c, slot[s], nullptr);
+        if (s == 0 && two_sets) {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || c->wsp[0].bytes() > total_b / 5) two_sets = false;
+        }
         busy[s] = (r == AW_OK);
         return r;
     };

@@ -128,9 +128,30 @@ struct KParams {
     uint8_t* bytes;
     unsigned long long* bytes_cursor;
     unsigned long long bytes_cap;
+    int solo_len;            // cluster kernels: sub-problems with plen + tlen below this run on CTA 0 of the cluster alone
 };
 
 // ------------------------------------------------------------------------------------------
+// Thread-block cluster helpers (Mb-scale pairs: one pair per cluster, see aw_align_kernel).  barrier.cluster with
+// release / acquire semantics orders global and distributed-shared-memory accesses of all CTAs of the cluster.
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// reads the int at the same shared-memory address in CTA `rank` of the cluster (DSMEM)
+__device__ __forceinline__ int ld_dsmem_int(const int* p, unsigned rank) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    unsigned ra;
+    int v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(ra) : "memory");
+    return v;
+}
+
 template <int NT>
 __device__ __forceinline__ void cta_sync() {
     if (NT == 32) __syncwarp();
@@ -951,9 +972,33 @@ __device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long
 // The kernel
 // ------------------------------------------------------------------------------------------
 //@region kernel prologue + pair setup
-template <int NT, int BITS, bool TWO, class WS>
+// leaving the DFS over sub-problems on failure.  In a cluster kernel a CTA that fails on its own (CTA 0 inside a solo
+// sub-problem, a backtrace or the CIGAR assembly) must keep popping sub-problems -- it drops the solo ones and meets the other
+// CTAs at the status exchange of the next cluster-wide one -- or the cluster would dead-lock on its next barrier.
+#define AW_DFS_FAIL            \
+    {                          \
+        if (CL > 1 && solo) continue; \
+        break;                 \
+    }
+#define AW_DFS_FAIL_CTA0       \
+    {                          \
+        if (CL > 1) continue;  \
+        break;                 \
+    }
+// CL > 1 (Mb-scale pairs, int32 chunked path only): one pair per thread-block CLUSTER of CL CTAs.  Every CTA runs the same
+// driver on replicated shared state (ring metadata, recursion stack, candidate lists); the cells of a wavefront step are split
+// over the warps of the whole cluster, one barrier.cluster per step replaces the CTA barrier, and each CTA then folds the
+// other CTAs' per-step reductions (trim ends, antidiagonal maxima, end cell, flags) into its own copy through distributed
+// shared memory -- so all CTAs keep taking identical decisions.  Sub-problems shorter than P.solo_len (the deep, narrow levels
+// of the biWFA recursion, where a cluster barrier per step would dominate) are left to CTA 0 alone, which also does every
+// backtrace and the CIGAR / PAF emission.  The wavefront rings stay in global memory (L2 / HBM): at Mb scale one ring row is
+// megabytes.
+template <int NT, int BITS, bool TWO, class WS, int CL = 1>
 __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const KParams P) {
+    static_assert(CL == 1 || (NT >= 64 && BITS == 2 && sizeof(WS) == 4), "cluster kernels exist for the int32 chunked path only");
     constexpr int NCOMP = TWO ? 5 : 3;
+    const unsigned crank = (CL > 1) ? cluster_ctarank() : 0u;  // this CTA's rank in its cluster
+    const unsigned cid = (CL > 1) ? blockIdx.x / CL : blockIdx.x;  // workspace / work-queue slot: one per cluster
     constexpr bool VEC = (NT >= 64) && (BITS == 2);        // chunked (16 bytes of cells per thread) wavefront loop
     constexpr bool SEQ_SMEM = VEC && sizeof(WS) == 2;      // int16-sized pairs: sequences staged in shared memory
     constexpr int CPT = 16 / sizeof(WS);                   // diagonals per thread in that loop: 8 int16 or 4 int32
@@ -971,6 +1016,8 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     __shared__ SubProblem stack[MAX_STACK];
     __shared__ unsigned s_next;
     __shared__ unsigned s_nruns;
+    __shared__ int s_rescan[NRED];   // wf_rescan's own reduction buffer (the step's buffer may still be read by other CTAs of a cluster)
+    __shared__ int s_cl_status;      // cluster kernels: this CTA's status, exchanged at the start of every cluster-wide sub-problem
     __shared__ int s_ncand, s_nact, s_ov[4];  // s_ov: thresholds for M / other components, first and last diagonal of any candidate
     constexpr int ACT_MAX = 256;
     __shared__ int s_act[ACT_MAX];            // blocks of aligner 0's wavefront that can hold a meeting point
@@ -982,7 +1029,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
 
     const int tid = threadIdx.x;
     const AwPen pen = P.pen;
-    int* const ws_i = P.ws + (size_t)blockIdx.x * P.ws_ints_per_cta;
+    int* const ws_i = P.ws + (size_t)cid * P.ws_ints_per_cta;
     WS* const ws = reinterpret_cast<WS*>(ws_i);  // all wavefront offsets below are in WS elements
     const int W = P.W;
     // int16 path: after the rings come one all-NULL row and the compact I/D rings (per direction e1+1 rows for each of
@@ -994,10 +1041,10 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     const int cmp_base = null_base + W;
     const int hist_base = VEC ? cmp_base + 2 * cmp_rows * W : null_base;  // history arena starts after the rings
     constexpr int VBW = VBLOCK_CHUNKS * CPT;  // diagonals per block of the per-block maxima
-    int* const blk_cta = VEC ? P.ws_blk + (size_t)blockIdx.x * 2 * ring_n * P.blk_cap * 2 : nullptr;
+    int* const blk_cta = VEC ? P.ws_blk + (size_t)cid * 2 * ring_n * P.blk_cap * 2 : nullptr;
     auto blk_of = [&](int d, int slot) -> int* { return blk_cta + (size_t)(d * ring_n + slot) * P.blk_cap * 2; };
-    int* const hist_meta = P.ws_hist_meta + (size_t)blockIdx.x * (size_t)P.hist_max_scores * HIST_META_INTS;
-    uint32_t* const pair_runs = P.ws_runs + (size_t)blockIdx.x * 2 * P.runs_cap;
+    int* const hist_meta = P.ws_hist_meta + (size_t)cid * (size_t)P.hist_max_scores * HIST_META_INTS;
+    uint32_t* const pair_runs = P.ws_runs + (size_t)cid * 2 * P.runs_cap;
     uint32_t* const leaf_runs = pair_runs + P.runs_cap;
 
     if constexpr (SEQ_SMEM) {
@@ -1006,6 +1053,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         if (tid == 0 && __cvta_generic_to_shared(s_seq2) + sizeof(s_seq2) > SEQ2_WINDOW) __trap();
     }
     for (int i = tid; i < 2 * 3 * NRED; i += NT) (&red[0][0][0])[i] = INT_MIN;
+    if (tid < NRED) s_rescan[tid] = INT_MIN;
     if constexpr (VEC) {
         const uint4 nv = make_uint4(VecT<WS>::NULLW, VecT<WS>::NULLW, VecT<WS>::NULLW, VecT<WS>::NULLW);
         for (int i = tid * CPT; i < W; i += NT * CPT) *reinterpret_cast<uint4*>(ws + null_base + i) = nv;
@@ -1024,11 +1072,37 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         red_i = (red_i + 1) % 3;
     };
 
+    // one wavefront-step barrier: CTA-wide, or cluster-wide followed by the fold of every CTA's reductions into this CTA's copy
+    // (max is idempotent, so a peer that reads a slot this CTA has already folded still ends with the same value; wf_rescan
+    // and rotate_red never touch the buffer of the current step, which peers may still be reading)
+    auto step_sync = [&](bool solo) {
+        if constexpr (CL > 1) {
+            if (!solo) {
+                cluster_sync_all();
+                if (tid < 2 * NRED) {
+                    int* slot = &red[tid / NRED][red_i][tid % NRED];
+                    int v = *slot;
+#pragma unroll
+                    for (unsigned r = 0; r < (unsigned)CL; ++r)
+                        if (r != crank) v = max(v, ld_dsmem_int(slot, r));
+                    *slot = v;
+                }
+            }
+        }
+        cta_sync<NT>();
+    };
     for (;;) {
-        if (tid == 0) s_next = atomicAdd(P.next_pair, 1u);
-        cta_sync<NT>();
-        const unsigned work_i = s_next;
-        cta_sync<NT>();
+        if (tid == 0 && crank == 0) s_next = atomicAdd(P.next_pair, 1u);
+        unsigned work_i;
+        if constexpr (CL > 1) {
+            cluster_sync_all();
+            work_i = (unsigned)ld_dsmem_int(reinterpret_cast<const int*>(&s_next), 0);
+            cluster_sync_all();  // CTA 0 may overwrite s_next only after everybody has read it
+        } else {
+            cta_sync<NT>();
+            work_i = s_next;
+            cta_sync<NT>();
+        }
         if (work_i >= P.npairs) break;
         const unsigned pair_i = P.order ? P.order[work_i] : work_i;
         const aw_pair pr = P.pairs[pair_i];
@@ -1036,7 +1110,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         if (is_rev > 1u) {
             // --wfa-orientation: one of the two orientation alignments ran out of workspace, the strand is undecided.
             // Nothing is aligned here; the host decides the strand with a larger workspace and re-runs the pair.
-            if (tid == 0) {
+            if (tid == 0 && crank == 0) {
                 AwPairOut o;
                 memset(&o, 0, sizeof(o));
                 o.status = AW_EWORKSPACE;
@@ -1059,7 +1133,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             const int np = PLEN / 16 + 2, ntt = TLEN / 16 + 2;
             seq_fits = SEQ_SMEM ? (2 * (np + ntt) <= SEQ2_ENTRIES) : ((unsigned long long)2 * (np + ntt) <= P.seq2_cap);
             // longer pairs keep the four arrays in a per-CTA global scratch (L1/L2-cached 8-byte loads)
-            uint2* s_pf = SEQ_SMEM ? s_seq2 : P.ws_seq2 + (size_t)blockIdx.x * P.seq2_cap;
+            uint2* s_pf = SEQ_SMEM ? s_seq2 : P.ws_seq2 + (size_t)cid * P.seq2_cap;
             uint2* s_tf = s_pf + np;
             uint2* s_pr = s_tf + ntt;
             uint2* s_tr = s_pr + np;
@@ -1182,7 +1256,10 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             int width;    // history mode: allocated elements per component
         };
         long long hist_used = 0;  // history arena bump pointer (base case)
-        auto v_launch = [&](int d, int mbase, int s, int slot, int gwarp, int gnw, bool hist, bool full, const SeqView& sv, int k_end, int comp_end) -> VRange {
+        // gwarp / gnw: this warp's index among / the number of warps that share the step (CTA-local, or cluster-wide when the
+        // sub-problem runs on the whole cluster); lwarp: its index among this CTA's warps of the step -- the first of them keeps
+        // the CTA's own copy of the ring metadata and of the step's range up to date
+        auto v_launch = [&](int d, int mbase, int s, int slot, int gwarp, int gnw, int lwarp, bool hist, bool full, const SeqView& sv, int k_end, int comp_end) -> VRange {
             constexpr int SH = (CPT == 8) ? 3 : 2;
             constexpr int MG = VMARGIN / CPT;
             const int lane = tid & 31;
@@ -1237,7 +1314,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             rg.lo = mlo;  // = wavefront_compute_limits_input over the non-empty inputs
             rg.hi = mhi;
             rg.width = 0;
-            const bool lead = (gwarp == 0);
+            const bool lead = (lwarp == 0);
             if (status != ST_OK) return rg;
             if (rg.lo > rg.hi) {  // null step
                 if (lead) {
@@ -1356,7 +1433,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
 #pragma unroll
                 for (int c = 0; c < 5; ++c) out[c] = mt.coff[(TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M];
                 StepOut so;
-                wf_rescan<NT, TWO, WS>(ws, out, clo, chi, plen, tlen, r, so);
+                wf_rescan<NT, TWO, WS>(ws, out, clo, chi, plen, tlen, s_rescan, so);
                 if (tid < 32) {
                     int wl = -VBIG, wh = VBIG;  // cells outside a component's trimmed range hold garbage: only the common part reads unmasked
 #pragma unroll
@@ -1443,9 +1520,33 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         };
 
 //@region subproblem setup
-        while (sp_n > 0 && status == ST_OK) {
+        while (sp_n > 0 && (status == ST_OK || CL > 1)) {
             const SubProblem sp = stack[--sp_n];
             const int plen = sp.pe - sp.pb, tlen = sp.te - sp.tb;
+            // cluster kernels: short sub-problems (and the trivial ones) belong to CTA 0 alone -- the other CTAs drop them
+            // and run ahead to the next cluster-wide sub-problem, where they wait for CTA 0
+            const bool solo = (CL > 1) && (tlen == 0 || plen == 0 || plen + tlen < P.solo_len);
+            const int cl_off = (CL > 1 && !solo) ? (int)crank : 0, cl_n = (CL > 1 && !solo) ? CL : 1;
+            if constexpr (CL > 1) {
+                if (solo) {
+                    if (crank != 0 || status != ST_OK) continue;
+                } else {
+                    // every CTA must enter a cluster-wide sub-problem with the same status (CTA 0 may have failed on its own);
+                    // the barriers also keep CTA 0's solo writes apart from the other CTAs' last reads of the rings
+                    // ... and with the same reduction-buffer rotation: CTA 0 has rotated its buffers through every solo step
+                    // since the last cluster-wide sub-problem, the others have not
+                    for (int i = tid; i < 2 * 3 * NRED; i += NT) (&red[0][0][0])[i] = INT_MIN;
+                    red_i = 0;
+                    if (tid == 0) s_cl_status = status;
+                    cluster_sync_all();
+                    int st = status;
+#pragma unroll
+                    for (unsigned r = 0; r < (unsigned)CL; ++r) st = max(st, ld_dsmem_int(&s_cl_status, r));
+                    cluster_sync_all();
+                    status = st;
+                    if (status != ST_OK) break;
+                }
+            }
             // ---- wavefront_bialign_alignment: trivial cases ----
             if (tlen == 0 || plen == 0) {
                 if (tid == 0) {
@@ -1795,10 +1896,11 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                         else if (first_full == INT_MAX) first_full = score_f + 1;
                         {
                             const int d = (warp < HW) ? 0 : 1;  // one call site for both directions (instruction-cache footprint)
-                            v_launch(d, d * ring_n, (d ? score_r : score_f) + 1, d ? slot_r : slot_f, d ? warp - HW : warp, HW, false, full, d ? svd[1] : svd[0], k_end,
-                                     d ? cend[1] : cend[0]);
+                            const int lw = d ? warp - HW : warp;
+                            v_launch(d, d * ring_n, (d ? score_r : score_f) + 1, d ? slot_r : slot_f, cl_off * HW + lw, cl_n * HW, lw, false, full,
+                                     d ? svd[1] : svd[0], k_end, d ? cend[1] : cend[0]);
                         }
-                        cta_sync<NT>();
+                        step_sync(solo);
                         bool dn[2];
                         int ak2[2];
 #pragma unroll 1
@@ -1867,8 +1969,9 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     bool done;
                     if constexpr (VEC) {
                         int ak;
-                        v_launch(d, d * ring_n, s, slot, tid >> 5, NT / 32, false, true, d == 0 ? svd[0] : svd[1], k_end, d == 0 ? cend[0] : cend[1]);
-                        cta_sync<NT>();
+                        v_launch(d, d * ring_n, s, slot, cl_off * (NT / 32) + (tid >> 5), cl_n * (NT / 32), tid >> 5, false, true, d == 0 ? svd[0] : svd[1], k_end,
+                                 d == 0 ? cend[0] : cend[1]);
+                        step_sync(solo);
                         done = v_finish(d, d * ring_n, slot, plen, tlen, k_end, d == 0 ? cend[0] : cend[1], ak);
                     } else {
                         const Range r = launch_dir(d, s, slot);
@@ -1907,7 +2010,10 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     a0 = d1;
                 }
                 lap(1);
-                if (status != ST_OK) break;
+                // cluster-wide sub-problem: nobody may write the rings again (CTA 0's next solo sub-problem) before every CTA
+                // has finished its last overlap scan
+                if (CL > 1 && !solo) cluster_sync_all();
+                if (status != ST_OK) AW_DFS_FAIL;
                 if (fb_end) {
                     do_base = true;
                 } else {
@@ -1915,7 +2021,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     const int bh = bp.off_f, bv = bp.off_f - bp.k_f;
                     if (bv < 0 || bv > plen || bh < 0 || bh > tlen || sp_n + 2 > MAX_STACK) {
                         status = ST_FAIL_WORKSPACE;
-                        break;
+                        AW_DFS_FAIL;
                     }
                     // right half is pushed first so that the left half is aligned (and emitted) first
                     SubProblem right = {sp.pb + bv, sp.pe, sp.tb + bh, sp.te, bp.comp, sp.ce, bp.score_r};
@@ -1968,9 +2074,9 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                             status = ST_FAIL_WORKSPACE;
                             break;
                         }
-                        const VRange rg = v_launch(0, 0, score, slot, tid >> 5, NT / 32, true, true, sv, k_end, sp.ce);
+                        const VRange rg = v_launch(0, 0, score, slot, cl_off * (NT / 32) + (tid >> 5), cl_n * (NT / 32), tid >> 5, true, true, sv, k_end, sp.ce);
                         hist_used += (long long)NCOMP * rg.width;
-                        cta_sync<NT>();
+                        step_sync(solo);
                         done = v_finish(0, 0, slot, plen, tlen, k_end, sp.ce, ak);
                         if (status != ST_OK) break;
                         write_hist_meta(score, ring_meta[slot]);
@@ -2071,7 +2177,9 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     done = end_reached(so, sp.ce, k_end, tlen);
                 }
                 }
-                if (status != ST_OK) break;
+                if (CL > 1 && !solo) cluster_sync_all();  // the whole history is in place (and see the note after phase 2)
+                if (status != ST_OK) AW_DFS_FAIL;
+                if (CL > 1 && crank != 0) continue;  // the backtrace and the CIGAR belong to CTA 0
                 w_maxbase = max(w_maxbase, (unsigned)score);
                 cta_sync<NT>();  // history + meta visible to warp 0
                 lap(2);
@@ -2183,14 +2291,14 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 cta_sync<NT>();
                 n_leaf = (unsigned)s_acc[0];
                 if (s_acc[1] != ST_OK) status = (int)s_acc[1];
-                if (status != ST_OK) break;
+                if (status != ST_OK) AW_DFS_FAIL_CTA0;
                 // append the leaf's runs (stored back to front) to the pair's CIGAR
                 unsigned base_n = s_nruns, skip = 0;
                 if (n_leaf > 0 && base_n > 0 && (pair_runs[base_n - 1] & 3u) == (leaf_runs[n_leaf - 1] & 3u)) skip = 1;
                 cta_sync<NT>();
                 if (base_n + n_leaf > P.runs_cap) {
                     status = ST_FAIL_WORKSPACE;
-                    break;
+                    AW_DFS_FAIL_CTA0;
                 }
                 if (tid == 0 && skip) pair_runs[base_n - 1] += leaf_runs[n_leaf - 1] & ~3u;
                 for (unsigned i = skip + tid; i < n_leaf; i += NT) pair_runs[base_n + i - skip] = leaf_runs[n_leaf - 1 - i];
@@ -2203,6 +2311,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
 //@region emit
         // =========== K8: statistics, score, PAF text ===========
         cta_sync<NT>();
+        if (CL > 1 && crank != 0) continue;  // CTA 0 owns the pair's CIGAR; the others go and wait for the next pair
         const unsigned nruns = (status == ST_OK) ? s_nruns : 0;
         if (tid < 8) s_acc[tid] = 0;
         cta_sync<NT>();
@@ -2355,6 +2464,9 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         }
         cta_sync<NT>();
     }
+    if constexpr (CL > 1) cluster_sync_all();  // no CTA may exit while another one can still read its shared memory
 }
+#undef AW_DFS_FAIL
+#undef AW_DFS_FAIL_CTA0
 
 }  // namespace awk

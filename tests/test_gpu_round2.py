@@ -331,3 +331,77 @@ def test_run_job_matches_cli_semantics(oracle, tmp_path):
     if aw._cabi.lib().aw_device_count() >= 2:
         r3 = H.run_job(ids, seqs, sparsification="none", n_gpus=2, checksum=True)
         assert r3["digest"] == r["digest"] and r3["pairs"] == r["pairs"]
+
+
+# ---- Mb-scale regime: one pair per thread-block cluster -----------------------------------------
+
+def _cluster_ctx(cluster_min_len, solo_len):
+    ctx = aw.Context(0)
+    ctx.set_option("cluster_min_len", cluster_min_len)
+    ctx.set_option("solo_len", solo_len)
+    return ctx
+
+
+@pytest.mark.parametrize("solo_len", [0, 3000, 40000])
+def test_cluster_kernel_parity(oracle, solo_len):
+    """the cluster kernel (8 CTAs per pair, wavefront cells split over the cluster, reductions folded through distributed
+    shared memory) on C4-shaped pairs short enough for the oracle: every sub-problem cluster-wide (solo_len 0), a mix, and
+    almost everything on CTA 0 -- each must give the oracle's PAF and the single-CTA kernel's"""
+    c, ids, seqs, _ = synth.config("C4", n=4, length=30000)
+    pairs = [(0, 1), (1, 2), (2, 3), (3, 0), (0, 2)]
+    exp = oracle.run_pairs(ids, seqs, pairs, oracle.params(**DEFAULT), use_mash=True, threads=CORES, fast=True)
+    ctx = _cluster_ctx(1000, solo_len)
+    try:
+        ctx.load_sequences(ids, seqs)
+        res = ctx.align_pairs(aw.make_params(**DEFAULT), pairs)
+        assert [r["status"] for r in res] == [0] * len(pairs)
+        assert [r["paf"] for r in res] == exp["paf"] and [r["score"] for r in res] == exp["scores"]
+    finally:
+        ctx.close()
+
+
+def test_cluster_kernel_edge_cases(oracle):
+    """pairs that end in the base case at once (identical, one long gap), affine single-piece penalties, wfa orientation"""
+    rnd = random.Random(77)
+    a = bytes(rnd.choice(b"ACGT") for _ in range(40000))
+    seqs = [a, a, a[:25000], a[5000:], _mutate(rnd, a, 0.01), oracle.reverse_complement(_mutate(rnd, a, 0.02))]
+    ids = ["k%d" % i for i in range(len(seqs))]
+    pairs = [(0, 1), (0, 2), (2, 0), (3, 0), (0, 4), (4, 5), (5, 0)]
+    ctx = _cluster_ctx(1000, 2000)
+    try:
+        ctx.load_sequences(ids, seqs)
+        for pen in (DEFAULT, dict(mismatch=4, gap_open=6, gap_extend=2, gap2_open=None, gap2_extend=None)):
+            exp = oracle.run_pairs(ids, seqs, pairs, oracle.params(**pen), use_mash=True, threads=CORES, fast=True)
+            res = ctx.align_pairs(aw.make_params(**pen), pairs)
+            assert [r["paf"] for r in res] == exp["paf"]
+    finally:
+        ctx.close()
+
+
+def test_c4_full_size_pairs_vs_golden():
+    """BASELINE config 4 as generated (200 x 1 Mb haplotypes, seed 4, SVs, giant:0.99): the first pairs of the list against the
+    frozen oracle results in tests/golden/c4_pairs.json.gz (tests/make_golden_c4.py; the oracle needs ~10 minutes per pair)"""
+    import gzip
+    import hashlib
+    import json
+
+    from allwave_b200 import hostlib as H
+
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c4_pairs.json.gz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/c4_pairs.json.gz has not been generated")
+    gold = json.load(gzip.open(path, "rt"))
+    c, ids, seqs, _ = synth.config("C4")
+    assert (c["seed"], c["n"], c["length"]) == (gold["seed"], gold["n"], gold["length"])
+    full = H.pair_list(ids, H.KIND_CONNECTIVITY, value=0.99)
+    assert len(full) == gold["n_pairs_in_list"] and hashlib.sha1(json.dumps([list(p) for p in full]).encode()).hexdigest() == gold["pair_list_sha1"]
+    pairs = [(g["q"], g["t"]) for g in gold["pairs"]]
+    assert pairs == [tuple(p) for p in full[: len(pairs)]]
+    ctx = aw.Context(0)
+    try:
+        ctx.load_sequences(ids, seqs)
+        res = ctx.align_pairs(aw.make_params(**DEFAULT), pairs)
+        for r, g in zip(res, gold["pairs"]):
+            assert r["status"] == 0 and r["score"] == g["score"] and r["paf"] == g["paf"], (g["q"], g["t"], r["score"], g["score"])
+    finally:
+        ctx.close()
