@@ -182,6 +182,7 @@ struct aw_ctx {
     int64_t chunk_pairs = 65536;
     int ws16 = 1;              // 1 = int16 wavefront storage when every offset fits
     int64_t cluster_min_len = 200000;  // pairs at least this long (2-bit sequences, int32 rows) run one pair per thread-block cluster; 0 = never
+    int cluster_always = 0;            // tests: use the cluster kernel whatever the batch size
     int64_t solo_len = 65536;          // ... and inside them sub-problems with plen + tlen below this are left to CTA 0 of the cluster
     int max_retry = 3;         // rungs of the retry ladder (0: a pair whose first-try workspace was too small fails)
     // streams: `stream` runs the kernels (they serialise: every launch fills the GPU), `up_stream` uploads the next batch's
@@ -372,6 +373,7 @@ extern "C" int aw_set_option(aw_ctx* c, const char* key, int64_t value) {
     else if (k == "band_engine") (void)value;  // accepted for compatibility: the experimental band engine of the first kernels is gone
     else if (k == "ws16") c->ws16 = value ? 1 : 0;
     else if (k == "cluster_min_len") c->cluster_min_len = value;
+    else if (k == "cluster_always") c->cluster_always = value ? 1 : 0;
     else if (k == "solo_len") c->solo_len = std::max<int64_t>(0, value);
     else if (k == "max_retry_attempts") c->max_retry = (int)std::max<int64_t>(0, std::min<int64_t>(3, value));
     else return AW_EINVAL;
@@ -920,7 +922,11 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     // (20 kb pairs, int32 rows: 571 pairs/s with 128 threads vs 501 with 256); Mb-scale pairs keep 256 threads per pair
     int nt = c->threads_per_cta ? c->threads_per_cta : (maxlen <= 1024 ? 32 : ((c->all_clean && (fits16 || maxlen <= 50000)) ? 128 : 256));
     // Mb-scale pairs: one pair per cluster of AW_CLUSTER_SIZE 256-thread CTAs (few pairs in flight, each on 2048 threads)
-    const bool use_cluster = c->cluster_min_len > 0 && c->all_clean && !fits16 && (int64_t)maxlen >= c->cluster_min_len && !c->threads_per_cta;
+    // ... when the batch is small: a cluster finishes one pair ~3x sooner than a single CTA but moves ~2.5x fewer cells per SM,
+    // so with enough pairs to occupy every CTA slot the one-CTA-per-pair kernel is the faster regime (profiles/README.md)
+    const uint64_t cluster_slots = std::max<uint64_t>(1, (uint64_t)c->sm_count * AW_CTAS_PER_SM(256) / AW_CLUSTER_SIZE);
+    const bool use_cluster = c->cluster_min_len > 0 && c->all_clean && !fits16 && (int64_t)maxlen >= c->cluster_min_len && !c->threads_per_cta &&
+                             (npairs <= 2 * cluster_slots || c->cluster_always);
     if (use_cluster) nt = 256;
     int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : AW_CTAS_PER_SM(nt));
     uint64_t full_w = (max_p + max_t + 3 + 16 + 15) & ~15ull;  // rows are 16-element aligned (vectorised int16 loop)

@@ -501,7 +501,7 @@ class AllPairIterator {
     // one per run, shared by all GPU threads: the cost-ordered pair list, the chunk cursor, the first error
     struct Shared {
         std::vector<aw_pair> pairs;
-        size_t chunk = 65536;
+        std::vector<size_t> chunk_begin;  // chunk c = pairs[chunk_begin[c] .. chunk_begin[c + 1])
         std::atomic<size_t> next{0};
         std::atomic<bool> cancel{false};
         std::mutex mu;  // serialises the user's callback (completion order, like the reference's rayon workers) and `err`
@@ -512,10 +512,10 @@ class AllPairIterator {
     static uint64_t next_chunk(void* user, const aw_pair** out) {
         Shared* sh = static_cast<Shared*>(user);
         if (sh->cancel.load(std::memory_order_relaxed)) return 0;
-        const size_t b = sh->next.fetch_add(sh->chunk);
-        if (b >= sh->pairs.size()) return 0;
-        *out = sh->pairs.data() + b;
-        return std::min(sh->chunk, sh->pairs.size() - b);
+        const size_t c = sh->next.fetch_add(1);
+        if (c + 1 >= sh->chunk_begin.size()) return 0;
+        *out = sh->pairs.data() + sh->chunk_begin[c];
+        return sh->chunk_begin[c + 1] - sh->chunk_begin[c];
     }
     static int fail(Shared* sh) {
         std::lock_guard<std::mutex> g(sh->mu);  // callers hold no lock
@@ -584,7 +584,18 @@ class AllPairIterator {
                 if (rco != AW_OK) throw std::runtime_error(std::string("aw_set_orientation_params: ") + aw_strerror(rco) + ": " + aw_last_error());
             }
         }
+        // chunks: a launch should carry enough pairs to keep its tail short -- reads by the hundred thousand, >= ~8 pairs per
+        // resident CTA for kb-scale pairs, one pair per resident CTA for Mb-scale pairs (which run for minutes each) -- and
+        // every GPU should get several chunks when there are enough pairs
+        size_t max_len = 0;
+        for (const auto& sq : seqs_) max_len = std::max(max_len, sq.seq.size());
+        const size_t lo = max_len <= 1024 ? 65536 : (max_len <= 50000 ? 4736 : 296), hi = max_len <= 1024 ? 262144 : 65536;
+        size_t n_chunks = chunk_pairs_ ? (n + chunk_pairs_ - 1) / chunk_pairs_ : std::max<size_t>(std::max<size_t>(g_n, (n + hi - 1) / hi), std::min<size_t>(12 * g_n, n / lo));
+        n_chunks = std::max<size_t>(1, std::min(n_chunks, n));
         if (g_n > 1) {
+            // several GPUs: order by predicted cost, heaviest first, and deal the list out to the chunks like cards (chunk c =
+            // pairs c, c + C, c + 2C, ... of the ordered list): every chunk carries the same cost mix, the shared queue absorbs
+            // what the prediction misses, and inside a launch the heavy pairs start first
             std::vector<float> div;
             if (use_mash_) {
                 div.resize(n);
@@ -596,16 +607,17 @@ class AllPairIterator {
                 costed[i] = {predicted_pair_cost(seqs_[sh.pairs[i].query_idx].seq.size(), seqs_[sh.pairs[i].target_idx].seq.size(), div.empty() ? 0.05 : (double)div[i]),
                              (uint32_t)i};
             std::stable_sort(costed.begin(), costed.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
-            std::vector<aw_pair> ordered(n);
-            for (size_t i = 0; i < n; ++i) ordered[i] = sh.pairs[costed[i].second];
+            std::vector<aw_pair> ordered;
+            ordered.reserve(n);
+            sh.chunk_begin.push_back(0);
+            for (size_t c = 0; c < n_chunks; ++c) {
+                for (size_t i = c; i < n; i += n_chunks) ordered.push_back(sh.pairs[costed[i].second]);
+                sh.chunk_begin.push_back(ordered.size());
+            }
             sh.pairs.swap(ordered);
+        } else {  // one GPU: the list stays in pair order (so does the output), cut into equal chunks
+            for (size_t c = 0; c <= n_chunks; ++c) sh.chunk_begin.push_back(c * n / n_chunks);
         }
-        // chunk size: large enough to fill a GPU many times over, small enough that every GPU gets >= ~12 chunks
-        // (a launch should carry >= ~8 pairs per resident CTA, or reads by the hundred thousand, to keep its tail short)
-        size_t max_len = 0;
-        for (const auto& s : seqs_) max_len = std::max(max_len, s.seq.size());
-        const size_t lo = max_len <= 1024 ? 65536 : 4736, hi = max_len <= 1024 ? 262144 : 65536;
-        sh.chunk = chunk_pairs_ ? chunk_pairs_ : std::min<size_t>(hi, std::max<size_t>(lo, (n + 12 * g_n - 1) / (12 * g_n)));
         std::vector<double> busy(g_n, 0.0);
         std::vector<int> rcs(g_n, AW_OK);
         std::vector<std::string> msgs(g_n);

@@ -338,6 +338,7 @@ def test_run_job_matches_cli_semantics(oracle, tmp_path):
 def _cluster_ctx(cluster_min_len, solo_len):
     ctx = aw.Context(0)
     ctx.set_option("cluster_min_len", cluster_min_len)
+    ctx.set_option("cluster_always", 1)
     ctx.set_option("solo_len", solo_len)
     return ctx
 
