@@ -863,16 +863,27 @@ __device__ __forceinline__ void wf_finish(const int* red, int lo, int hi, StepOu
 
 //@region wf_rescan
 // exact trim of every component by re-reading the stored wavefront (rare slow path)
+// `tt` / `tn`: this thread's index in / the size of the team that owns the row -- the whole CTA, or one warp (wm) when the
+// warps of a CTA work on different base cases at the same time
 template <int NT, bool TWO, class WS>
-__device__ __noinline__ void wf_rescan(const WS* __restrict__ ws, const int (&out)[5], int lo, int hi, int plen_, int tlen_, int* red, StepOut& so) {
+__device__ __noinline__ void wf_rescan(const WS* __restrict__ ws, const int (&out)[5], int lo, int hi, int plen_, int tlen_, int* red, StepOut& so, int tt, int tn,
+                                       bool wm) {
     const unsigned tlen = (unsigned)tlen_, plen = (unsigned)plen_;
-    cta_sync<NT>();
-    if (threadIdx.x < NRED) red[threadIdx.x] = INT_MIN;
-    cta_sync<NT>();
+    auto tsync = [&]() {
+        if (wm) __syncwarp();
+        else cta_sync<NT>();
+    };
+    auto tmax = [&](int idx, int v) {
+        v = __reduce_max_sync(0xffffffffu, v);
+        if ((threadIdx.x & 31) == 0 && v != INT_MIN) atomicMax(&red[idx], v);
+    };
+    tsync();
+    if (tt < NRED) red[tt] = INT_MIN;
+    tsync();
     int vhi[5], vlo[5];
 #pragma unroll
     for (int c = 0; c < 5; ++c) vhi[c] = vlo[c] = INT_MIN;
-    for (int k = lo + (int)threadIdx.x; k <= hi; k += NT) {
+    for (int k = lo + tt; k <= hi; k += tn) {
 #pragma unroll
         for (int c = 0; c < 5; ++c) {
             if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
@@ -886,10 +897,10 @@ __device__ __noinline__ void wf_rescan(const WS* __restrict__ ws, const int (&ou
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
-        red_max<NT>(red, RED_HI + c, vhi[c]);
-        red_max<NT>(red, RED_LO + c, vlo[c]);
+        tmax(RED_HI + c, vhi[c]);
+        tmax(RED_LO + c, vlo[c]);
     }
-    cta_sync<NT>();
+    tsync();
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
         if (!TWO && (c == AW_COMP_I2 || c == AW_COMP_D2)) continue;
@@ -903,9 +914,9 @@ __device__ __noinline__ void wf_rescan(const WS* __restrict__ ws, const int (&ou
         }
     }
     so.ambiguous = false;
-    cta_sync<NT>();
-    if (threadIdx.x < NRED) red[threadIdx.x] = INT_MIN;
-    cta_sync<NT>();
+    tsync();
+    if (tt < NRED) red[tt] = INT_MIN;
+    tsync();
 }
 
 //@region misc helpers
@@ -1007,12 +1018,25 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     const int scope = P.pen.scope;
     const int ring_n = scope + 1;  // one spare slot: the reverse step is computed speculatively
     SlotMeta* ring_meta = reinterpret_cast<SlotMeta*>(smem_raw);                                     // [2][ring_n]
-    int* cand = reinterpret_cast<int*>(ring_meta + 2 * ring_n);                                     // [scope*5] candidate tests
+    int* cand = reinterpret_cast<int*>(ring_meta + ((VEC && CL == 1) ? 2 + NT / 32 : 2) * ring_n);  // [scope*5] candidate tests (after the SlotMeta rings)
     int* hitk = cand + scope * 5;                                                                    // [scope*5] first hit per candidate
     unsigned long long* scanbuf = reinterpret_cast<unsigned long long*>(hitk + scope * 5);  // [NT]; 8-byte aligned: sizeof(SlotMeta)*2*ring_n + 40*scope
     int* cklo = reinterpret_cast<int*>(scanbuf + NT);                                      // [scope*5] first diagonal of a candidate's scan range
     int* ckhi = cklo + scope * 5;                                                          // [scope*5] last diagonal
-    __shared__ int red[2][3][NRED];
+    // warp-parallel leaves (LEAFPAR): the base cases (score_remaining <= 250) of a pair are independent of each other, narrow
+    // (<= 501 diagonals) and cost one CTA barrier per score when the whole CTA works on one of them -- with three of four
+    // warps idle.  They are collected in DFS order and run NW at a time, ONE WARP EACH (chunked engine with a team of one
+    // warp, __syncwarp instead of the CTA barrier, own slice of the history arena), then appended to the CIGAR in order.
+    constexpr bool LEAFPAR = VEC && CL == 1;
+    constexpr int NW = NT / 32;
+    constexpr int RM_N = LEAFPAR ? 2 + NW : 2;  // SlotMeta rings: forward, reverse (row 0 doubles as the cooperative base case) + one per warp
+    __shared__ int red[RM_N][3][NRED];
+    __shared__ int s_rescan_w[LEAFPAR ? NW : 1][NRED];
+    __shared__ SubProblem s_leaf[LEAFPAR ? NW : 1];
+    __shared__ unsigned s_leaf_n[LEAFPAR ? NW : 1];                 // per leaf: runs, status, score, work counters
+    __shared__ int s_leaf_st[LEAFPAR ? NW : 1], s_leaf_score[LEAFPAR ? NW : 1];
+    __shared__ unsigned long long s_leaf_cells[LEAFPAR ? NW : 1];
+    __shared__ unsigned s_leaf_steps[LEAFPAR ? NW : 1];
     __shared__ SubProblem stack[MAX_STACK];
     __shared__ unsigned s_next;
     __shared__ unsigned s_nruns;
@@ -1052,8 +1076,9 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         // inside (launch_align pads the dynamic part so that the CTA owns at least that much)
         if (tid == 0 && __cvta_generic_to_shared(s_seq2) + sizeof(s_seq2) > SEQ2_WINDOW) __trap();
     }
-    for (int i = tid; i < 2 * 3 * NRED; i += NT) (&red[0][0][0])[i] = INT_MIN;
+    for (int i = tid; i < RM_N * 3 * NRED; i += NT) (&red[0][0][0])[i] = INT_MIN;
     if (tid < NRED) s_rescan[tid] = INT_MIN;
+    if (LEAFPAR && (tid & 31) < NRED) s_rescan_w[tid >> 5][tid & 31] = INT_MIN;
     if constexpr (VEC) {
         const uint4 nv = make_uint4(VecT<WS>::NULLW, VecT<WS>::NULLW, VecT<WS>::NULLW, VecT<WS>::NULLW);
         for (int i = tid * CPT; i < W; i += NT * CPT) *reinterpret_cast<uint4*>(ws + null_base + i) = nv;
@@ -1062,10 +1087,26 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     cta_sync<NT>();
 
     auto comp_idx = [](int c) -> int { return TWO ? c : (c == AW_COMP_D1 ? 2 : c); };
+    // team context of the step lambdas below: the whole CTA, or -- while a batch of leaves is being aligned -- one warp
+    bool wm = false;                 // warp mode
+    int t_tid = tid;                 // thread index inside the team
+    int t_d = 0;                     // warp mode: this warp's row of red[] (its SlotMeta ring is ring_meta[t_d * ring_n ...])
+    int hb_cur = hist_base;          // history arena of the team: first element, capacity, metadata rows, leaf run buffer
+    long long hcap_cur = P.hist_ints;
+    int* hmeta_cur = hist_meta;
+    int hscores_cur = P.hist_max_scores;
+    uint32_t* lruns_cur = leaf_runs;
+    unsigned long long lcap_cur = P.runs_cap;
+    auto team_sync = [&]() {
+        if (wm) __syncwarp();
+        else cta_sync<NT>();
+    };
     auto rotate_red = [&]() {
         // recycle the buffers used two steps ago (everybody finished reading them before the last barrier)
         const int nxt = (red_i + 2) % 3;
-        if (tid < NRED) {
+        if (wm) {
+            if (t_tid < NRED) red[t_d][nxt][t_tid] = INT_MIN;
+        } else if (tid < NRED) {
             red[0][nxt][tid] = INT_MIN;
             red[1][nxt][tid] = INT_MIN;
         }
@@ -1354,8 +1395,8 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             } else {
                 const int clo = (c_lo - MG) << SH;
                 rg.width = (c_hi - c_lo + 1 + 2 * MG) << SH;
-                fail = (hist_used + (long long)NCOMP * rg.width > (long long)P.hist_ints);
-                out_off = hist_base + (int)hist_used - clo;
+                fail = (hist_used + (long long)NCOMP * rg.width > hcap_cur);
+                out_off = hb_cur + (int)hist_used - clo;
                 cstride = rg.width;
                 wlo = clo;
                 whi = clo + rg.width - 1;
@@ -1433,8 +1474,8 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
 #pragma unroll
                 for (int c = 0; c < 5; ++c) out[c] = mt.coff[(TWO || c == AW_COMP_M || c == AW_COMP_I1 || c == AW_COMP_D1) ? c : AW_COMP_M];
                 StepOut so;
-                wf_rescan<NT, TWO, WS>(ws, out, clo, chi, plen, tlen, s_rescan, so);
-                if (tid < 32) {
+                wf_rescan<NT, TWO, WS>(ws, out, clo, chi, plen, tlen, (LEAFPAR && wm) ? s_rescan_w[tid >> 5] : s_rescan, so, t_tid, wm ? 32 : NT, wm);
+                if (t_tid < 32) {
                     int wl = -VBIG, wh = VBIG;  // cells outside a component's trimmed range hold garbage: only the common part reads unmasked
 #pragma unroll
                     for (int c = 0; c < 5; ++c) {
@@ -1448,9 +1489,9 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     mt.wlo = wl;
                     mt.whi = wh;
                 }
-                cta_sync<NT>();
+                team_sync();
             }
-            if (tid < 32) {
+            if (t_tid < 32) {
                 mt.akM = akM;
                 mt.akAll = akAll;
             }
@@ -1470,13 +1511,13 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 cstride = W;
             } else {
                 cstride = chi - clo + 1;
-                out_off = hist_base - clo;
+                out_off = hb_cur - clo;
                 hist_used = (long long)NCOMP * cstride;
             }
             if constexpr (VEC) {
                 WS* row = ws + out_off + comp_idx(cb) * cstride;
-                if (tid <= 2 * MG) {
-                    const int kc = (tid - MG) << SH;
+                if (t_tid <= 2 * MG) {
+                    const int kc = (t_tid - MG) << SH;
                     uint32_t v[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) v[i] = VecT<WS>::NULLW;
@@ -1493,13 +1534,13 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     if (kc >= clo && kc + CPT - 1 <= chi) st_vec<WS>(row + kc, v);
                 }
             }
-            if (tid < 32) {
-                if (tid < 5) {
-                    mt.lo[tid] = (tid == cb) ? 0 : 1;
-                    mt.hi[tid] = 0;
+            if (t_tid < 32) {
+                if (t_tid < 5) {
+                    mt.lo[t_tid] = (t_tid == cb) ? 0 : 1;
+                    mt.hi[t_tid] = 0;
                 }
-                if (tid < 5) mt.coff[tid] = out_off + comp_idx(tid) * cstride;
-                if (tid == 5) {
+                if (t_tid < 5) mt.coff[t_tid] = out_off + comp_idx(t_tid) * cstride;
+                if (t_tid == 5) {
                     mt.off = out_off;
                     mt.cstride = cstride;
                     mt.wlo = clo;
@@ -1509,9 +1550,9 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     mt.nblk = 1;
                 }
             }
-            cta_sync<NT>();
+            team_sync();
             const int akM = r[RED_AKM], endval = r[RED_END];
-            if (tid < 32) {
+            if (t_tid < 32) {
                 mt.akM = akM;
                 mt.akAll = r[RED_AKALL];
             }
@@ -1519,8 +1560,243 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
             return k_end == 0 && endval >= sv.tlen;  // only component cb is non-empty, at k = 0
         };
 
+        // ---- base-case helpers, team-aware (the whole CTA or one warp, see LEAFPAR) ----
+        auto write_hist_meta = [&](int s, const SlotMeta& m) {
+            if (t_tid == 0) {
+                int* g = hmeta_cur + (size_t)s * HIST_META_INTS;
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    g[c] = m.lo[c];
+                    g[5 + c] = m.hi[c];
+                }
+                g[10] = m.off;
+                g[11] = m.cstride;
+            }
+        };
+        // wavefront_backtrace_affine by ONE warp (all 32 lanes call it): lanes evaluate the nine candidates; returns the number of
+        // runs pushed, back to front, into the team's leaf run buffer
+        auto bt_run = [&](int ce_, int score_, int plen_, int tlen_, int k_end_) -> unsigned {
+            const int lane = tid & 31;
+            unsigned n_leaf = 0;
+            unsigned last_run = 0;  // pending run (merged before being stored)
+            auto push = [&](unsigned op, unsigned len) {
+                if (len == 0) return;
+                if (last_run != 0 && (last_run & 3u) == op) {
+                    last_run += len << 2;
+                } else {
+                    if (last_run != 0) {
+                        if (lane == 0 && n_leaf < lcap_cur) lruns_cur[n_leaf] = last_run;
+                        ++n_leaf;
+                    }
+                    last_run = (len << 2) | op;
+                }
+            };
+            int type = ce_, sc = score_, k = k_end_, offset = tlen_;
+            int v = plen_, h = tlen_;
+            // lane l evaluates backtrace candidate type l+1 (AW_BT_*)
+            while (v > 0 && h > 0 && sc > 0) {
+                const int bt = lane + 1;
+                int cand_v = INT_MIN;
+                if (lane < 9) {
+                    int comp_src, cost, dk, add;
+                    bool active;
+                    switch (bt) {
+                        case AW_BT_M: comp_src = AW_COMP_M; cost = pen.x; dk = 0; add = 1; active = (type == AW_COMP_M); break;
+                        case AW_BT_I1_OPEN: comp_src = AW_COMP_M; cost = pen.o1 + pen.e1; dk = -1; add = 1; active = (type == AW_COMP_M || type == AW_COMP_I1); break;
+                        case AW_BT_I1_EXT: comp_src = AW_COMP_I1; cost = pen.e1; dk = -1; add = 1; active = (type == AW_COMP_M || type == AW_COMP_I1); break;
+                        case AW_BT_I2_OPEN: comp_src = AW_COMP_M; cost = pen.o2 + pen.e2; dk = -1; add = 1; active = TWO && (type == AW_COMP_M || type == AW_COMP_I2); break;
+                        case AW_BT_I2_EXT: comp_src = AW_COMP_I2; cost = pen.e2; dk = -1; add = 1; active = TWO && (type == AW_COMP_M || type == AW_COMP_I2); break;
+                        case AW_BT_D1_OPEN: comp_src = AW_COMP_M; cost = pen.o1 + pen.e1; dk = 1; add = 0; active = (type == AW_COMP_M || type == AW_COMP_D1); break;
+                        case AW_BT_D1_EXT: comp_src = AW_COMP_D1; cost = pen.e1; dk = 1; add = 0; active = (type == AW_COMP_M || type == AW_COMP_D1); break;
+                        case AW_BT_D2_OPEN: comp_src = AW_COMP_M; cost = pen.o2 + pen.e2; dk = 1; add = 0; active = TWO && (type == AW_COMP_M || type == AW_COMP_D2); break;
+                        default: comp_src = AW_COMP_D2; cost = pen.e2; dk = 1; add = 0; active = TWO && (type == AW_COMP_M || type == AW_COMP_D2); break;
+                    }
+                    const int ss = sc - cost;
+                    if (active && ss >= 0) {
+                        const int* g = hmeta_cur + (size_t)ss * HIST_META_INTS;
+                        const int kk = k + dk;
+                        if (g[comp_src] <= kk && kk <= g[5 + comp_src]) {
+                            const int val = ws[g[10] + comp_idx(comp_src) * g[11] + kk];
+                            if (val >= 0) cand_v = ((val + add) << AW_BT_TYPE_BITS) | bt;
+                        }
+                    }
+                }
+                const int max_all = __reduce_max_sync(0xffffffffu, cand_v);
+                if (max_all == INT_MIN) {  // cannot happen on a valid path
+                    status = ST_FAIL_WORKSPACE;
+                    break;
+                }
+                if (type == AW_COMP_M) {
+                    const int max_offset = max_all >> AW_BT_TYPE_BITS;
+                    push(AW_OP_M, (unsigned)max(0, offset - max_offset));
+                    offset = max_offset;
+                    v = offset - k;
+                    h = offset;
+                    if (v <= 0 || h <= 0) break;
+                }
+                const int b = max_all & 0xF;
+                switch (b) {
+                    case AW_BT_M: sc -= pen.x; type = AW_COMP_M; break;
+                    case AW_BT_I1_OPEN: sc -= pen.o1 + pen.e1; type = AW_COMP_M; break;
+                    case AW_BT_I1_EXT: sc -= pen.e1; type = AW_COMP_I1; break;
+                    case AW_BT_I2_OPEN: sc -= pen.o2 + pen.e2; type = AW_COMP_M; break;
+                    case AW_BT_I2_EXT: sc -= pen.e2; type = AW_COMP_I2; break;
+                    case AW_BT_D1_OPEN: sc -= pen.o1 + pen.e1; type = AW_COMP_M; break;
+                    case AW_BT_D1_EXT: sc -= pen.e1; type = AW_COMP_D1; break;
+                    case AW_BT_D2_OPEN: sc -= pen.o2 + pen.e2; type = AW_COMP_M; break;
+                    default: sc -= pen.e2; type = AW_COMP_D2; break;
+                }
+                if (b == AW_BT_M) {
+                    push(AW_OP_X, 1);
+                    --offset;
+                } else if (b <= AW_BT_I2_EXT) {
+                    push(AW_OP_I, 1);
+                    --k;
+                    --offset;
+                } else {
+                    push(AW_OP_D, 1);
+                    ++k;
+                }
+                v = offset - k;
+                h = offset;
+            }
+            if (v > 0 && h > 0) {
+                const int nm = min(v, h);
+                push(AW_OP_M, (unsigned)nm);
+                v -= nm;
+                h -= nm;
+            }
+            if (v > 0) push(AW_OP_D, (unsigned)v);
+            if (h > 0) push(AW_OP_I, (unsigned)h);
+            if (last_run != 0) {
+                if (lane == 0 && n_leaf < lcap_cur) lruns_cur[n_leaf] = last_run;
+                ++n_leaf;
+            }
+            return n_leaf;
+        };
+
+        // ---- LEAFPAR: align the pending leaves, one warp each, then append their runs in DFS order ----
+        int n_pending = 0;
+        auto flush_leaves = [&]() {
+            if constexpr (LEAFPAR) {
+                cta_sync<NT>();  // s_leaf is complete; no cooperative step is in flight
+                const int w = tid >> 5, lane = tid & 31;
+                if (w < n_pending) {
+                    const SubProblem lf = s_leaf[w];
+                    const int lp = lf.pe - lf.pb, lt = lf.te - lf.tb;
+                    unsigned n_leaf = 0;
+                    int lscore = -1;
+                    const unsigned long long cells0 = w_cells;
+                    const unsigned steps0 = w_steps;
+                    // the team is this warp: its own SlotMeta ring and reduction row, a slice of the history arena, of the
+                    // history metadata and of the leaf run buffer
+                    wm = true;
+                    t_tid = lane;
+                    t_d = 2 + w;
+                    red_i = 0;
+                    hcap_cur = (long long)((P.hist_ints / NW) & ~15);
+                    hb_cur = hist_base + w * (int)hcap_cur;
+                    hscores_cur = P.hist_max_scores / NW;
+                    hmeta_cur = hist_meta + (size_t)w * hscores_cur * HIST_META_INTS;
+                    lcap_cur = P.runs_cap / NW;
+                    lruns_cur = leaf_runs + (size_t)w * lcap_cur;
+                    hist_used = 0;
+                    if (lt == 0 || lp == 0) {  // wavefront_bialign_alignment's trivial cases: one pure gap
+                        const unsigned len = (unsigned)(lt == 0 ? lp : lt);
+                        if (len) {
+                            if (lane == 0) lruns_cur[0] = (len << 2) | (lt == 0 ? AW_OP_D : AW_OP_I);
+                            n_leaf = 1;
+                        }
+                    } else {
+                        const int k_end = lt - lp;
+                        const SeqView sv = SeqView{reinterpret_cast<const uint32_t*>(pf2), reinterpret_cast<const uint32_t*>(tf2), lf.pb, lf.tb, lp, lt, false};
+                        for (int i = lane; i < 3 * NRED; i += 32) (&red[t_d][0][0])[i] = INT_MIN;
+                        __syncwarp();
+                        const int mbase = t_d * ring_n;
+                        int ak, score = 0, slot = 0;
+                        bool done = v_init_row(t_d, mbase, true, sv, lf.cb, lf.ce, k_end, ak);
+                        write_hist_meta(0, ring_meta[mbase]);
+                        rotate_red();
+                        while (!done) {
+                            ++score;
+                            slot = (slot + 1 == ring_n) ? 0 : slot + 1;
+                            if (score >= hscores_cur) {
+                                status = ST_FAIL_WORKSPACE;
+                                break;
+                            }
+                            const VRange rg = v_launch(t_d, mbase, score, slot, 0, 1, 0, true, true, sv, k_end, lf.ce);
+                            hist_used += (long long)NCOMP * rg.width;
+                            __syncwarp();
+                            done = v_finish(t_d, mbase, slot, lp, lt, k_end, lf.ce, ak);
+                            if (status != ST_OK) break;
+                            write_hist_meta(score, ring_meta[mbase + slot]);
+                            rotate_red();
+                        }
+                        __syncwarp();  // the warp's history rows and metadata are visible to all of its lanes
+                        if (status == ST_OK) n_leaf = bt_run(lf.ce, score, lp, lt, k_end);
+                        lscore = score;
+                    }
+                    if (lane == 0) {
+                        s_leaf_n[w] = n_leaf;
+                        s_leaf_st[w] = status;
+                        s_leaf_score[w] = lscore;
+                        s_leaf_cells[w] = w_cells - cells0;
+                        s_leaf_steps[w] = w_steps - steps0;
+                    }
+                    w_cells = cells0;  // every thread adds every leaf's work below, so that the counters stay CTA-uniform
+                    w_steps = steps0;
+                    wm = false;
+                    t_tid = tid;
+                    t_d = 0;
+                    hb_cur = hist_base;
+                    hcap_cur = P.hist_ints;
+                    hscores_cur = P.hist_max_scores;
+                    hmeta_cur = hist_meta;
+                    lcap_cur = P.runs_cap;
+                    lruns_cur = leaf_runs;
+                }
+                cta_sync<NT>();
+                for (int q = 0; q < n_pending; ++q) {
+                    status = max(status, s_leaf_st[q]);
+                    w_cells += s_leaf_cells[q];
+                    w_steps += s_leaf_steps[q];
+                    if (s_leaf_score[q] >= 0) {
+                        ++w_base;
+                        w_maxbase = max(w_maxbase, (unsigned)s_leaf_score[q]);
+                    }
+                }
+                for (int i = tid; i < RM_N * 3 * NRED; i += NT) (&red[0][0][0])[i] = INT_MIN;  // the warps rotated their rows on their own
+                red_i = 0;
+                const unsigned long long lpart = P.runs_cap / NW;
+                for (int q = 0; q < n_pending && status == ST_OK; ++q) {
+                    // append leaf q's runs (stored back to front) to the pair's CIGAR, merging with the last run when the op continues
+                    const uint32_t* lr = leaf_runs + (size_t)q * lpart;
+                    const unsigned n_leaf = s_leaf_n[q];
+                    const unsigned base_n = s_nruns;
+                    unsigned skip = 0;
+                    if (n_leaf > 0 && base_n > 0 && (pair_runs[base_n - 1] & 3u) == (lr[n_leaf - 1] & 3u)) skip = 1;
+                    cta_sync<NT>();
+                    if (n_leaf > lpart || base_n + n_leaf > P.runs_cap) {
+                        status = ST_FAIL_WORKSPACE;
+                        break;
+                    }
+                    if (tid == 0 && skip) pair_runs[base_n - 1] += lr[n_leaf - 1] & ~3u;
+                    for (unsigned i = skip + tid; i < n_leaf; i += NT) pair_runs[base_n + i - skip] = lr[n_leaf - 1 - i];
+                    if (tid == 0) s_nruns = base_n + n_leaf - skip;
+                    cta_sync<NT>();
+                }
+                n_pending = 0;
+                cta_sync<NT>();
+            }
+        };
+
 //@region subproblem setup
-        while (sp_n > 0 && (status == ST_OK || CL > 1)) {
+        bool flush_req = false;  // LEAFPAR: the pending leaves must be appended before the sub-problem on top of the stack runs
+        for (;;) {
+            // the single call site of flush_leaves (instruction-cache footprint): a full batch, a request, or the end of the DFS
+            if (LEAFPAR && n_pending > 0 && status == ST_OK && (n_pending == NW || flush_req || sp_n == 0)) flush_leaves();
+            flush_req = false;
+            if (!(sp_n > 0 && (status == ST_OK || CL > 1))) break;
             const SubProblem sp = stack[--sp_n];
             const int plen = sp.pe - sp.pb, tlen = sp.te - sp.tb;
             // cluster kernels: short sub-problems (and the trivial ones) belong to CTA 0 alone -- the other CTAs drop them
@@ -1545,6 +1821,15 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     cluster_sync_all();
                     status = st;
                     if (status != ST_OK) break;
+                }
+            }
+            if constexpr (LEAFPAR) {
+                // trivial sub-problems and base cases are leaves of the recursion: they wait until NW of them can run side by side
+                // (rem == -1 marks an END_REACHED fallback that was put back: it runs cooperatively, see below)
+                if (tlen == 0 || plen == 0 || (sp.rem <= AW_BIALIGN_FALLBACK_MIN_SCORE && sp.rem != -1)) {
+                    if (tid == 0) s_leaf[n_pending] = sp;
+                    ++n_pending;
+                    continue;
                 }
             }
             // ---- wavefront_bialign_alignment: trivial cases ----
@@ -1675,7 +1960,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     if (so.ambiguous) {
                         int out[5];
                         out_offsets(d, slot, out);
-                        wf_rescan<NT, TWO, WS>(ws, out, r.lo, r.hi, plen, tlen, red[d][red_i], so);
+                        wf_rescan<NT, TWO, WS>(ws, out, r.lo, r.hi, plen, tlen, red[d][red_i], so, tid, NT, false);
                     }
                     store_meta(mt, so);
                     return end_reached(so, d == 0 ? cend[0] : cend[1], k_end, tlen);
@@ -2036,6 +2321,16 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
 //@region base case
             // =========== K7: wavefront_bialign_base: full-history WFA + backtrace ===========
             {
+                if (LEAFPAR && n_pending) {
+                    // this base case (an END_REACHED fallback) comes after the pending leaves in CIGAR order: put it back, marked,
+                    // and let the top of the loop flush them first
+                    SubProblem again = sp;
+                    again.rem = -1;
+                    stack[sp_n++] = again;
+                    flush_req = true;
+                    cta_sync<NT>();
+                    continue;
+                }
                 ++w_base;
                 lap(5);
                 const SeqView sv = VEC ? SeqView{reinterpret_cast<const uint32_t*>(pf2), reinterpret_cast<const uint32_t*>(tf2), sp.pb, sp.tb, plen, tlen, false}
@@ -2043,18 +2338,6 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 hist_used = 0;
                 // component block of a history wavefront: element (c,k) at ws[hist_off(off,width,clo,c) + k]
                 auto hist_off = [&](int off, int width, int clo, int c) -> int { return hist_base + off + comp_idx(c) * width - clo; };
-                auto write_hist_meta = [&](int s, const SlotMeta& m) {
-                    if (tid == 0) {
-                        int* g = hist_meta + (size_t)s * HIST_META_INTS;
-#pragma unroll
-                        for (int c = 0; c < 5; ++c) {
-                            g[c] = m.lo[c];
-                            g[5 + c] = m.hi[c];
-                        }
-                        g[10] = m.off;
-                        g[11] = m.cstride;
-                    }
-                };
                 auto slot_back = [&](int slot, int back) -> int {
                     const int s = slot - back;
                     return s < 0 ? s + ring_n : s;
@@ -2070,7 +2353,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     while (!done) {
                         ++score;
                         slot = (slot + 1 == ring_n) ? 0 : slot + 1;
-                        if (score >= P.hist_max_scores) {
+                        if (score >= hscores_cur) {
                             status = ST_FAIL_WORKSPACE;
                             break;
                         }
@@ -2167,7 +2450,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                     wf_cells<NT, BITS, TWO, WS>(ws, in, out, lo, hi, sv, k_end, sp.ce, red[0][red_i]);
                     cta_sync<NT>();
                     wf_finish<TWO>(red[0][red_i], lo, hi, so);
-                    if (so.ambiguous) wf_rescan<NT, TWO, WS>(ws, out, lo, hi, plen, tlen, red[0][red_i], so);
+                    if (so.ambiguous) wf_rescan<NT, TWO, WS>(ws, out, lo, hi, plen, tlen, red[0][red_i], so, tid, NT, false);
                     w_cells += (unsigned long long)(hi - lo + 1) * NCOMP;
                     store_meta(mt, so);
                     mt.off = hist_off(off, width, clo, AW_COMP_M);
@@ -2188,102 +2471,8 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 // ---- wavefront_backtrace_affine by warp 0: lanes evaluate the candidates ----
                 unsigned n_leaf = 0;  // runs pushed (reverse order) into leaf_runs; uniform within warp 0
                 if (tid < 32) {
-                    const int lane = tid;
-                    unsigned last_run = 0;  // pending run (merged before being stored)
-                    auto push = [&](unsigned op, unsigned len) {
-                        if (len == 0) return;
-                        if (last_run != 0 && (last_run & 3u) == op) {
-                            last_run += len << 2;
-                        } else {
-                            if (last_run != 0) {
-                                if (lane == 0 && n_leaf < P.runs_cap) leaf_runs[n_leaf] = last_run;
-                                ++n_leaf;
-                            }
-                            last_run = (len << 2) | op;
-                        }
-                    };
-                    int type = sp.ce, sc = score, k = k_end, offset = tlen;
-                    int v = plen, h = tlen;
-                    // lane l evaluates backtrace candidate type l+1 (AW_BT_*)
-                    while (v > 0 && h > 0 && sc > 0) {
-                        const int bt = lane + 1;
-                        int cand_v = INT_MIN;
-                        if (lane < 9) {
-                            int comp_src, cost, dk, add;
-                            bool active;
-                            switch (bt) {
-                                case AW_BT_M: comp_src = AW_COMP_M; cost = pen.x; dk = 0; add = 1; active = (type == AW_COMP_M); break;
-                                case AW_BT_I1_OPEN: comp_src = AW_COMP_M; cost = pen.o1 + pen.e1; dk = -1; add = 1; active = (type == AW_COMP_M || type == AW_COMP_I1); break;
-                                case AW_BT_I1_EXT: comp_src = AW_COMP_I1; cost = pen.e1; dk = -1; add = 1; active = (type == AW_COMP_M || type == AW_COMP_I1); break;
-                                case AW_BT_I2_OPEN: comp_src = AW_COMP_M; cost = pen.o2 + pen.e2; dk = -1; add = 1; active = TWO && (type == AW_COMP_M || type == AW_COMP_I2); break;
-                                case AW_BT_I2_EXT: comp_src = AW_COMP_I2; cost = pen.e2; dk = -1; add = 1; active = TWO && (type == AW_COMP_M || type == AW_COMP_I2); break;
-                                case AW_BT_D1_OPEN: comp_src = AW_COMP_M; cost = pen.o1 + pen.e1; dk = 1; add = 0; active = (type == AW_COMP_M || type == AW_COMP_D1); break;
-                                case AW_BT_D1_EXT: comp_src = AW_COMP_D1; cost = pen.e1; dk = 1; add = 0; active = (type == AW_COMP_M || type == AW_COMP_D1); break;
-                                case AW_BT_D2_OPEN: comp_src = AW_COMP_M; cost = pen.o2 + pen.e2; dk = 1; add = 0; active = TWO && (type == AW_COMP_M || type == AW_COMP_D2); break;
-                                default: comp_src = AW_COMP_D2; cost = pen.e2; dk = 1; add = 0; active = TWO && (type == AW_COMP_M || type == AW_COMP_D2); break;
-                            }
-                            const int ss = sc - cost;
-                            if (active && ss >= 0) {
-                                const int* g = hist_meta + (size_t)ss * HIST_META_INTS;
-                                const int kk = k + dk;
-                                if (g[comp_src] <= kk && kk <= g[5 + comp_src]) {
-                                    const int val = ws[g[10] + comp_idx(comp_src) * g[11] + kk];
-                                    if (val >= 0) cand_v = ((val + add) << AW_BT_TYPE_BITS) | bt;
-                                }
-                            }
-                        }
-                        const int max_all = __reduce_max_sync(0xffffffffu, cand_v);
-                        if (max_all == INT_MIN) {  // cannot happen on a valid path
-                            status = ST_FAIL_WORKSPACE;
-                            break;
-                        }
-                        if (type == AW_COMP_M) {
-                            const int max_offset = max_all >> AW_BT_TYPE_BITS;
-                            push(AW_OP_M, (unsigned)max(0, offset - max_offset));
-                            offset = max_offset;
-                            v = offset - k;
-                            h = offset;
-                            if (v <= 0 || h <= 0) break;
-                        }
-                        const int b = max_all & 0xF;
-                        switch (b) {
-                            case AW_BT_M: sc -= pen.x; type = AW_COMP_M; break;
-                            case AW_BT_I1_OPEN: sc -= pen.o1 + pen.e1; type = AW_COMP_M; break;
-                            case AW_BT_I1_EXT: sc -= pen.e1; type = AW_COMP_I1; break;
-                            case AW_BT_I2_OPEN: sc -= pen.o2 + pen.e2; type = AW_COMP_M; break;
-                            case AW_BT_I2_EXT: sc -= pen.e2; type = AW_COMP_I2; break;
-                            case AW_BT_D1_OPEN: sc -= pen.o1 + pen.e1; type = AW_COMP_M; break;
-                            case AW_BT_D1_EXT: sc -= pen.e1; type = AW_COMP_D1; break;
-                            case AW_BT_D2_OPEN: sc -= pen.o2 + pen.e2; type = AW_COMP_M; break;
-                            default: sc -= pen.e2; type = AW_COMP_D2; break;
-                        }
-                        if (b == AW_BT_M) {
-                            push(AW_OP_X, 1);
-                            --offset;
-                        } else if (b <= AW_BT_I2_EXT) {
-                            push(AW_OP_I, 1);
-                            --k;
-                            --offset;
-                        } else {
-                            push(AW_OP_D, 1);
-                            ++k;
-                        }
-                        v = offset - k;
-                        h = offset;
-                    }
-                    if (v > 0 && h > 0) {
-                        const int nm = min(v, h);
-                        push(AW_OP_M, (unsigned)nm);
-                        v -= nm;
-                        h -= nm;
-                    }
-                    if (v > 0) push(AW_OP_D, (unsigned)v);
-                    if (h > 0) push(AW_OP_I, (unsigned)h);
-                    if (last_run != 0) {
-                        if (lane == 0 && n_leaf < P.runs_cap) leaf_runs[n_leaf] = last_run;
-                        ++n_leaf;
-                    }
-                    if (lane == 0) {
+                    n_leaf = bt_run(sp.ce, score, plen, tlen, k_end);
+                    if (tid == 0) {
                         s_acc[0] = n_leaf;
                         s_acc[1] = (unsigned long long)status;
                     }
