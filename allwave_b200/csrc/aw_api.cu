@@ -873,7 +873,7 @@ cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStrea
 cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bool ws16, int grid, cudaStream_t st, int cluster = 1) {
     const int scope = P.pen.scope;
     // SlotMeta rings: forward + reverse, plus one per warp for the warp-parallel leaves of the chunked kernels (aw_wfa.cuh RM_N)
-    const int rm_n = (nt >= 64 && bits == 2 && cluster == 1) ? 2 + nt / 32 : 2;
+    const int rm_n = (AW_LEAFPAR && nt >= 64 && bits == 2 && cluster == 1) ? 2 + nt / 32 : 2;
     size_t smem = sizeof(awk::SlotMeta) * rm_n * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt + sizeof(int) * (10 * scope + 4);
     if (cluster == AW_CLUSTER_SIZE && nt == 256 && bits == 2 && !ws16) {
         if (two) return launch_align<256, 2, true, int, AW_CLUSTER_SIZE>(P, grid, smem, st);

@@ -43,6 +43,9 @@ namespace awk {
 #ifndef AW_CYCLE_COUNTERS
 #define AW_CYCLE_COUNTERS 0  // (build with -DAW_CYCLE_COUNTERS=1 for tools/perf_probe.py) per-phase device-clock breakdown in AwPairOut::cyc (aw_batch_debug_cycles); 0 frees ~14 registers
 #endif
+#ifndef AW_LEAFPAR
+#define AW_LEAFPAR 1  // warp-parallel leaves (see LEAFPAR in aw_align_kernel); 0 = every base case on the whole CTA (tuning builds)
+#endif
 #ifndef AW_REGS
 #define AW_REGS 128  // register budget per thread of the CTA-per-pair kernels: resident CTAs per SM = 65536 / (NT * AW_REGS)
 #endif
@@ -1018,7 +1021,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     const int scope = P.pen.scope;
     const int ring_n = scope + 1;  // one spare slot: the reverse step is computed speculatively
     SlotMeta* ring_meta = reinterpret_cast<SlotMeta*>(smem_raw);                                     // [2][ring_n]
-    int* cand = reinterpret_cast<int*>(ring_meta + ((VEC && CL == 1) ? 2 + NT / 32 : 2) * ring_n);  // [scope*5] candidate tests (after the SlotMeta rings)
+    int* cand = reinterpret_cast<int*>(ring_meta + ((AW_LEAFPAR && VEC && CL == 1) ? 2 + NT / 32 : 2) * ring_n);  // [scope*5] candidate tests (after the SlotMeta rings)
     int* hitk = cand + scope * 5;                                                                    // [scope*5] first hit per candidate
     unsigned long long* scanbuf = reinterpret_cast<unsigned long long*>(hitk + scope * 5);  // [NT]; 8-byte aligned: sizeof(SlotMeta)*2*ring_n + 40*scope
     int* cklo = reinterpret_cast<int*>(scanbuf + NT);                                      // [scope*5] first diagonal of a candidate's scan range
@@ -1027,7 +1030,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
     // (<= 501 diagonals) and cost one CTA barrier per score when the whole CTA works on one of them -- with three of four
     // warps idle.  They are collected in DFS order and run NW at a time, ONE WARP EACH (chunked engine with a team of one
     // warp, __syncwarp instead of the CTA barrier, own slice of the history arena), then appended to the CIGAR in order.
-    constexpr bool LEAFPAR = VEC && CL == 1;
+    constexpr bool LEAFPAR = AW_LEAFPAR && VEC && CL == 1;
     constexpr int NW = NT / 32;
     constexpr int RM_N = LEAFPAR ? 2 + NW : 2;  // SlotMeta rings: forward, reverse (row 0 doubles as the cooperative base case) + one per warp
     __shared__ int red[RM_N][3][NRED];
