@@ -4,6 +4,7 @@
 // the path runs in the kernels of aw_wfa.cuh / aw_sketch.cuh; there is no CPU fallback.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -840,6 +841,7 @@ cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStrea
     }
     // int16 2-bit kernels read the staged sequences through a 32 KB address window (ld16s): the CTA must own all of it
     if (NT >= 64 && BITS == 2 && sizeof(WS) == 2 && static_smem + smem < awk::SEQ2_WINDOW) smem = awk::SEQ2_WINDOW - static_smem;
+    if (const char* pad = getenv("AW_SMEM_PAD")) smem += (size_t)atoi(pad);  // tuning aid: what does a larger shared-memory footprint cost?
     if (static_smem + smem > (size_t)max_optin) return cudaErrorInvalidConfiguration;
     if (static_smem + smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

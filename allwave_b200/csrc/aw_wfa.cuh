@@ -37,6 +37,9 @@ namespace awk {
 #ifndef AW_PREFETCH_NEXT_ITER
 #define AW_PREFETCH_NEXT_ITER 1  // chunked path: prefetch (L1) the rows of a warp's next iteration while it computes the current one
 #endif
+#ifndef AW_PF_DIST32
+#define AW_PF_DIST32 1  // int32 rows: prefetch distance (warp iterations) of the row loads, into L2 (measured on 296 x 100 kb pairs: 1: 17.0 s, 4: 17.6 s, 8: 18.6 s, 16: 18.8 s)
+#endif
 #ifndef AW_LOAD_CG
 #define AW_LOAD_CG 0  // chunked path: 1 = row loads bypass L1 (ld.global.cg)
 #endif
@@ -611,18 +614,33 @@ __device__ __noinline__ void wf_cells_v(WS* __restrict__ ws, int in_off, const i
                     ld_vec<WS>(at(kc, o_i2e), ie2);
                     ld_vec<WS>(at(kc, o_d2e), de2);
                 }
-                if (AW_PREFETCH_NEXT_ITER && cw + gnw * OWN <= c_hi) {
-                    // this warp's next iteration reads the same rows gnw*OWN chunks further on: request those lines now so that
-                    // only the first iteration of a step waits for L2 / HBM
-                    const int kn = kc + gnw * OWN * CPT;
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_mx)));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_mo1)));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_i1e)));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_d1e)));
-                    if (TWO) {
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_mo2)));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_i2e)));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_d2e)));
+                // this warp's later iterations read the same rows further on: request those lines now so that only the first
+                // iteration(s) of a step wait for L2 / HBM.  int16 rows (kb-scale pairs, a few iterations per step): the next
+                // iteration, into L1.  int32 rows (Mb-scale pairs stream rows of megabytes through HBM, hundreds of iterations per
+                // warp and step): AW_PF_DIST32 iterations ahead, into L2 (L1 is too small to hold that many lines per warp).
+                constexpr int PFD = SSEQ ? 1 : AW_PF_DIST32;
+                if (AW_PREFETCH_NEXT_ITER && cw + PFD * gnw * OWN <= c_hi) {
+                    const int kn = kc + PFD * gnw * OWN * CPT;
+                    if constexpr (SSEQ) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_mx)));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_mo1)));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_i1e)));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_d1e)));
+                        if (TWO) {
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_mo2)));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_i2e)));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(at(kn, o_d2e)));
+                        }
+                    } else {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(at(kn, o_mx)));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(at(kn, o_mo1)));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(at(kn, o_i1e)));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(at(kn, o_d1e)));
+                        if (TWO) {
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(at(kn, o_mo2)));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(at(kn, o_i2e)));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(at(kn, o_d2e)));
+                        }
                     }
                 }
             } else {

@@ -592,8 +592,9 @@ class AllPairIterator {
         const size_t lo = max_len <= 1024 ? 65536 : (max_len <= 50000 ? 4736 : 296), hi = max_len <= 1024 ? 262144 : 65536;
         size_t n_chunks = chunk_pairs_ ? (n + chunk_pairs_ - 1) / chunk_pairs_ : std::max<size_t>(std::max<size_t>(g_n, (n + hi - 1) / hi), std::min<size_t>(12 * g_n, n / lo));
         n_chunks = std::max<size_t>(1, std::min(n_chunks, n));
-        if (g_n > 1) {
-            // several GPUs: order by predicted cost, heaviest first, and deal the list out to the chunks like cards (chunk c =
+        if (g_n > 1 && max_len > 1024) {
+            // several GPUs (reads up to 1 kb cost about the same each: no ordering, the queue alone balances them):
+            // order by predicted cost, heaviest first, and deal the list out to the chunks like cards (chunk c =
             // pairs c, c + C, c + 2C, ... of the ordered list): every chunk carries the same cost mix, the shared queue absorbs
             // what the prediction misses, and inside a launch the heavy pairs start first
             std::vector<float> div;

@@ -42,7 +42,7 @@ CONFIGS = {
     "C3": dict(desc="C3: 1415 x 150 bp reads, 2% divergence, -p none (2,000,810 directed pairs), -s 0,1,1,1, mash orientation",
                scores=(0, 1, 1, 1, None, None), spars="none", batch=2000810, cpu_pairs_per_core=20000, dtype="int32"),
     "C4": dict(desc="C4: 200 x 1 Mb haplotypes, 0.1-2% divergence + SVs, -p giant:0.99 (~1,970 pairs), -s 0,5,8,2,24,1, mash orientation",
-               scores=(0, 5, 8, 2, 24, 1), spars="giant:0.99", batch=0, cpu_pairs_per_core=0, dtype="int32"),
+               scores=(0, 5, 8, 2, 24, 1), spars="giant:0.99", batch=16, cpu_pairs_per_core=0, dtype="int32"),  # 16 pairs: one per cluster, ~40 s per step
     "C5": dict(desc="C5: 5000 x 5 kb, 3% divergence, 50% reverse-complemented, -p tree:2:1:0.1 (~2.51 M pairs), -s 0,5,8,2,24,1, mash orientation",
                scores=(0, 5, 8, 2, 24, 1), spars="tree:2:1:0.1", batch=37888, cpu_pairs_per_core=64, dtype="int16"),
 }
