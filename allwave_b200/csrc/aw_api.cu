@@ -810,7 +810,12 @@ extern "C" int aw_batch_create(aw_ctx* c, const aw_params* params, int orientati
 namespace {
 
 // Mb-scale pairs: CTAs per pair (thread-block cluster; 8 is the largest portable cluster size)
-#define AW_CLUSTER_SIZE 8
+#ifndef AW_CLUSTER_SIZE
+#define AW_CLUSTER_SIZE 8  // (16 needs the non-portable cluster size opt-in)
+#endif
+#ifndef AW_CLUSTER_NT
+#define AW_CLUSTER_NT 512  // threads per CTA of the cluster kernels: 4 pairs of 1 Mb take 23.8 s with 512, 35.5 s with 256
+#endif
 
 struct LaunchCfg {
     int nt, grid;
@@ -848,6 +853,10 @@ cudaError_t launch_align(const awk::KParams& P, int grid, size_t smem, cudaStrea
         if (e != cudaSuccess) return e;
     }
     if (CL > 1) {  // one pair per thread-block cluster
+        if (CL > 8) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+        }
         cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3((unsigned)grid);
         lc.blockDim = dim3(NT);
@@ -877,10 +886,10 @@ cudaError_t dispatch_align(const awk::KParams& P, int nt, int bits, bool two, bo
     // SlotMeta rings: forward + reverse, plus one per warp for the warp-parallel leaves of the chunked kernels (aw_wfa.cuh RM_N)
     const int rm_n = (AW_LEAFPAR && nt >= 64 && bits == 2 && cluster == 1) ? 2 + nt / 32 : 2;
     size_t smem = sizeof(awk::SlotMeta) * rm_n * (scope + 1) + sizeof(int) * 10 * scope + sizeof(unsigned long long) * nt + sizeof(int) * (10 * scope + 4);
-    if (cluster == AW_CLUSTER_SIZE && nt == 256 && bits == 2 && !ws16) {
-        if (two) return launch_align<256, 2, true, int, AW_CLUSTER_SIZE>(P, grid, smem, st);
+    if (cluster == AW_CLUSTER_SIZE && nt == AW_CLUSTER_NT && bits == 2 && !ws16) {
+        if (two) return launch_align<AW_CLUSTER_NT, 2, true, int, AW_CLUSTER_SIZE>(P, grid, smem, st);
 #ifndef AW_FAST_BUILD
-        return launch_align<256, 2, false, int, AW_CLUSTER_SIZE>(P, grid, smem, st);
+        return launch_align<AW_CLUSTER_NT, 2, false, int, AW_CLUSTER_SIZE>(P, grid, smem, st);
 #endif
     }
     if (cluster != 1) return cudaErrorInvalidConfiguration;
@@ -928,10 +937,10 @@ int plan_launch(aw_ctx* c, const AwPen& pen, uint64_t npairs, uint64_t max_p, ui
     // Mb-scale pairs: one pair per cluster of AW_CLUSTER_SIZE 256-thread CTAs (few pairs in flight, each on 2048 threads)
     // ... when the batch is small: a cluster finishes one pair ~3x sooner than a single CTA but moves ~2.5x fewer cells per SM,
     // so with enough pairs to occupy every CTA slot the one-CTA-per-pair kernel is the faster regime (profiles/README.md)
-    const uint64_t cluster_slots = std::max<uint64_t>(1, (uint64_t)c->sm_count * AW_CTAS_PER_SM(256) / AW_CLUSTER_SIZE);
+    const uint64_t cluster_slots = std::max<uint64_t>(1, (uint64_t)c->sm_count * AW_CTAS_PER_SM(AW_CLUSTER_NT) / AW_CLUSTER_SIZE);
     const bool use_cluster = c->cluster_min_len > 0 && c->all_clean && !fits16 && (int64_t)maxlen >= c->cluster_min_len && !c->threads_per_cta &&
                              (npairs <= 2 * cluster_slots || c->cluster_always);
-    if (use_cluster) nt = 256;
+    if (use_cluster) nt = AW_CLUSTER_NT;
     int per_sm = c->ctas_per_sm ? c->ctas_per_sm : (nt == 32 ? 16 : AW_CTAS_PER_SM(nt));
     uint64_t full_w = (max_p + max_t + 3 + 16 + 15) & ~15ull;  // rows are 16-element aligned (vectorised int16 loop)
     uint64_t W = full_w;

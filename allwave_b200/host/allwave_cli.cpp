@@ -102,9 +102,8 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "error: the argument '--keep-prefixes <KEEP_PREFIXES>' cannot be used with '--exclude-prefixes <EXCLUDE_PREFIXES>'\n");
         return 2;
     }
-    // -t: the reference's rayon pool size.  Here the pairs run on the GPU(s); the host always uses one driver thread per GPU
-    // plus one writer thread, so -t only matters as "more than one worker": it allows cost-ordered (out-of-order) scheduling
-    // on a single GPU exactly like --gpus N does (the reference's output order is unspecified for -t > 1 as well).
+    // -t: the reference's rayon pool size.  Accepted for command-line compatibility; the pairs run on the GPU(s), and the host
+    // always uses one driver thread per GPU plus one writer thread whatever -t says.
     (void)threads;
     if (input.empty()) {
         std::fprintf(stderr, "error: -i/--input is required\n");

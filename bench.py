@@ -38,7 +38,7 @@ CONFIGS = {
     "C1": dict(desc="C1: 16 x 10 kb, 1% divergence per haplotype, -p none (240 directed pairs), -s 0,5,8,2,24,1, mash orientation",
                scores=(0, 5, 8, 2, 24, 1), spars="none", batch=240, cpu_pairs_per_core=15, dtype="int16"),
     "C2": dict(desc="C2: 1000 x 10 kb, 5% divergence per haplotype, -p none (999,000 directed pairs), -s 0,5,8,2,24,1, mash orientation",
-               scores=(0, 5, 8, 2, 24, 1), spars="none", batch=9472, cpu_pairs_per_core=8, dtype="int16"),
+               scores=(0, 5, 8, 2, 24, 1), spars="none", batch=14208, cpu_pairs_per_core=8, dtype="int16"),  # 24 pairs per resident CTA: short tail
     "C3": dict(desc="C3: 1415 x 150 bp reads, 2% divergence, -p none (2,000,810 directed pairs), -s 0,1,1,1, mash orientation",
                scores=(0, 1, 1, 1, None, None), spars="none", batch=2000810, cpu_pairs_per_core=20000, dtype="int32"),
     "C4": dict(desc="C4: 200 x 1 Mb haplotypes, 0.1-2% divergence + SVs, -p giant:0.99 (~1,970 pairs), -s 0,5,8,2,24,1, mash orientation",
