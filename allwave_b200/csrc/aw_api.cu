@@ -650,8 +650,8 @@ extern "C" int aw_estimate_divergence(aw_ctx* c, const aw_pair* pairs, uint64_t 
 // create_wfa_aligner + AlignmentMode::from_params (src/alignment.rs:263-289, src/types.rs:105-117)
 static int pen_from_params(const aw_params* p, AwPen* pen) {
     memset(pen, 0, sizeof(*pen));
-    if (p->match_score != 0) {
-        aw_set_error("match_score != 0 is not supported (WFA2 penalty shifting is out of scope)");
+    if (p->match_score > 0) {
+        aw_set_error("match_score must be negative or zero (WFA2: wavefront_penalties_set_*)");
         return AW_EUNSUPPORTED;
     }
     const bool two = p->has_gap2_open && p->has_gap2_extend;
@@ -668,6 +668,22 @@ static int pen_from_params(const aw_params* p, AwPen* pen) {
     if (pen->x <= 0 || pen->o1 < 0 || pen->e1 <= 0) {
         aw_set_error("penalties must satisfy mismatch>0, gap_open>=0, gap_extend>0");
         return AW_EINVAL;
+    }
+    pen->sx = pen->x;
+    pen->so1 = pen->o1;
+    pen->se1 = pen->e1;
+    pen->so2 = pen->o2;
+    pen->se2 = pen->e2;
+    pen->smatch = p->match_score;
+    if (p->match_score < 0) {  // WFA2's penalty shifting (include/aw_wfa2_compat.h): the wavefronts run on x', o', e'
+        const int m = p->match_score;
+        pen->x = AW_SHIFT_MISMATCH(pen->x, m);
+        pen->o1 = AW_SHIFT_GAP_OPEN(pen->o1, m);
+        pen->e1 = AW_SHIFT_GAP_EXTEND(pen->e1, m);
+        if (two) {
+            pen->o2 = AW_SHIFT_GAP_OPEN(pen->o2, m);
+            pen->e2 = AW_SHIFT_GAP_EXTEND(pen->e2, m);
+        }
     }
     int sc = std::max(pen->x, pen->o1 + pen->e1);
     if (two) sc = std::max(sc, pen->o2 + pen->e2);

@@ -23,9 +23,12 @@ struct AwSlot {
 
 // WFA2 penalties after create_wfa_aligner's mode mapping (src/alignment.rs:263-289)
 struct AwPen {
-    int x, o1, e1, o2, e2;
+    int x, o1, e1, o2, e2;  // what the wavefronts run on: the user's penalties, or AW_SHIFT_* of them when match_score < 0
     int two_piece;
     int scope;  // max_score_scope = max(x, o1+e1, o2+e2) + 1
+    // the user's own penalties, for the reported score of the final CIGAR (cigar_score_gap_affine*): equal to the above when
+    // match_score == 0
+    int sx, so1, se1, so2, se2, smatch;
 };
 
 // CIGAR run: (len << 2) | op, op: 0=M 1=X 2=I 3=D (WFA2 letters)

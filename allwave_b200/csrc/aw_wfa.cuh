@@ -2532,10 +2532,11 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
                 const unsigned long long len = run >> 2;
                 cnt[op] += len;
                 textlen += ndigits(len) + 1;
-                if (op == AW_OP_X) penalty += len * pen.x;
+                // score of the final CIGAR under the user's own penalties (they differ from pen.x ... when match_score < 0)
+                if (op == AW_OP_X) penalty += len * pen.sx;
                 else if (op != AW_OP_M) {
-                    unsigned long long c1 = pen.o1 + len * pen.e1;
-                    if (TWO) c1 = min(c1, pen.o2 + len * (unsigned long long)pen.e2);
+                    unsigned long long c1 = pen.so1 + len * pen.se1;
+                    if (TWO) c1 = min(c1, pen.so2 + len * (unsigned long long)pen.se2);
                     penalty += c1;
                 }
             }
@@ -2652,7 +2653,7 @@ __global__ void __launch_bounds__(NT, AW_CTAS_PER_SM(NT)) aw_align_kernel(const 
         if (tid == 0) {
             AwPairOut o;
             o.status = (status == ST_OK) ? AW_OK : AW_EWORKSPACE;
-            o.score = (status == ST_OK) ? -(int32_t)penalty : INT_MAX;
+            o.score = (status == ST_OK) ? (int32_t)(-(long long)penalty - (long long)pen.smatch * (long long)n_m) : INT_MAX;
             o.is_reverse = is_rev;
             o.nruns = nruns;
             o.n_m = n_m;

@@ -38,7 +38,7 @@ typedef enum aw_status {
     AW_ENODEVICE = -2,     /* no usable CUDA device / CUDA runtime error at init */
     AW_ECUDA = -3,         /* CUDA runtime error (see aw_last_error) */
     AW_ENOMEM = -4,        /* host or device allocation failed */
-    AW_EUNSUPPORTED = -5,  /* e.g. match_score != 0, unknown orientation mode */
+    AW_EUNSUPPORTED = -5,  /* e.g. match_score > 0, max_score_scope > 512 */
     AW_EWORKSPACE = -6,    /* internal per-pair status: device workspace too small, the pair is re-run by the retry ladder
                               (a pair that still fails after the ladder is delivered as AW_EALIGN + failure sentinel) */
     AW_ECALLBACK = -7,     /* the user callback returned non-zero; run cancelled */

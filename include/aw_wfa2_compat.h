@@ -34,6 +34,15 @@
  * max(o1, o2) for gap-affine-2p. */
 #define AW_BIALIGN_GAP_OPENING(two_piece, o1, o2) ((two_piece) ? ((o1) > (o2) ? (o1) : (o2)) : (o1))
 
+/* wavefront_penalties_set_affine / _affine2p with a match score M < 0 (a bonus): WFA2 aligns with shifted penalties
+ *   x' = 2x - 2M,  o' = 2o,  e' = 2e - M        (every column of the alignment gives up M/2 per consumed character)
+ * which ranks global alignments exactly like the original scoring, and reports the score of the final CIGAR under the
+ * ORIGINAL penalties: score = -(x*#X + sum of gap costs) - M*#M  (= -(s' + M*(plen+tlen)) / 2 for the shifted penalty s').
+ * M > 0 is rejected.  [recalled from wavefront_penalties.c / cigar_score_gap_affine*; see PARITY UNPINNED above] */
+#define AW_SHIFT_MISMATCH(x, m) (2 * (x) - 2 * (m))
+#define AW_SHIFT_GAP_OPEN(o, m) (2 * (o))
+#define AW_SHIFT_GAP_EXTEND(e, m) (2 * (e) - (m))
+
 /* wavefront_compute_process_ends: trim the [lo,hi] of every output component (1) or of M only (0) */
 #define AW_TRIM_ALL_COMPONENTS 1
 

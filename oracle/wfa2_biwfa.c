@@ -814,10 +814,11 @@ int awo_mode_from_params(const awo_params_t* p) {
 }
 
 /* create_wfa_aligner (src/alignment.rs:263-289) -> WFA2 penalties */
-static int pen_from_params(const awo_params_t* p, pen_t* pen) {
+/* `shifted` = the penalties the wavefronts run on (AW_SHIFT_* when match < 0); otherwise the user's own, for scoring the CIGAR */
+static int pen_from_params_ex(const awo_params_t* p, pen_t* pen, int shifted) {
     memset(pen, 0, sizeof(*pen));
     const int mode = awo_mode_from_params(p);
-    if (p->match_score != 0) return -1; /* WFA2 penalty shifting for match<0 is out of scope */
+    if (p->match_score > 0) return -1; /* wavefront_penalties_set_*: the match score must be negative or zero */
     pen->x = p->mismatch_penalty;
     if (mode == AWO_MODE_EDIT) {
         pen->o1 = p->mismatch_penalty;
@@ -833,12 +834,24 @@ static int pen_from_params(const awo_params_t* p, pen_t* pen) {
         if (pen->o2 < 0 || pen->e2 <= 0) return -1;
     }
     if (pen->x <= 0 || pen->o1 < 0 || pen->e1 <= 0) return -1;
+    if (shifted && p->match_score < 0) {
+        const int m = p->match_score;
+        pen->x = AW_SHIFT_MISMATCH(pen->x, m);
+        pen->o1 = AW_SHIFT_GAP_OPEN(pen->o1, m);
+        pen->e1 = AW_SHIFT_GAP_EXTEND(pen->e1, m);
+        if (pen->two_piece) {
+            pen->o2 = AW_SHIFT_GAP_OPEN(pen->o2, m);
+            pen->e2 = AW_SHIFT_GAP_EXTEND(pen->e2, m);
+        }
+    }
     return 0;
 }
+static int pen_from_params(const awo_params_t* p, pen_t* pen) { return pen_from_params_ex(p, pen, 1); }
 
+/* penalty of a CIGAR under the user's own penalties, matches included (cigar_score_gap_affine*): -score */
 int64_t awo_cigar_penalty(const awo_params_t* params, const uint8_t* ops, size_t n) {
     pen_t pn;
-    if (pen_from_params(params, &pn)) return -1;
+    if (pen_from_params_ex(params, &pn, 0)) return INT64_MIN;
     int64_t total = 0;
     size_t i = 0;
     while (i < n) {
@@ -846,7 +859,8 @@ int64_t awo_cigar_penalty(const awo_params_t* params, const uint8_t* ops, size_t
         size_t j = i;
         while (j < n && ops[j] == op) ++j;
         int64_t L = (int64_t)(j - i);
-        if (op == 'X') total += L * pn.x;
+        if (op == 'M') total += L * params->match_score;
+        else if (op == 'X') total += L * pn.x;
         else if (op == 'I' || op == 'D') {
             int64_t c1 = pn.o1 + L * pn.e1;
             if (pn.two_piece) {

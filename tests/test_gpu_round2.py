@@ -406,3 +406,21 @@ def test_c4_full_size_pairs_vs_golden():
             assert r["status"] == 0 and r["score"] == g["score"] and r["paf"] == g["paf"], (g["q"], g["t"], r["score"], g["score"])
     finally:
         ctx.close()
+
+
+def test_match_score_bonus(oracle, gpu_ctx):
+    """match_score < 0: WFA2 shifts the penalties (x' = 2x - 2M, o' = 2o, e' = 2e - M; include/aw_wfa2_compat.h) and reports
+    the CIGAR's score under the user's own penalties.  Same op strings, cg and scores as the oracle; match > 0 is refused."""
+    ids, seqs, pairs = _sweep_group(977, nfam=24, members=4, maxlen=320, npairs=2500)
+    for pen in (dict(match=-1, mismatch=4, gap_open=6, gap_extend=2, gap2_open=None, gap2_extend=None),
+                dict(match=-2, mismatch=5, gap_open=8, gap_extend=2, gap2_open=24, gap2_extend=1),
+                dict(match=-3, mismatch=2, gap_open=1, gap_extend=1, gap2_open=None, gap2_extend=None)):
+        res = _paf_parity(oracle, gpu_ctx, ids, seqs, pairs, pen)
+        assert any(r["score"] > 0 for r in res)        # a bonus makes near-identical pairs score positive
+    ids2, seqs2, _ = synth.generate(12, 6, 9000, 0.04)
+    pairs2 = [(i, j) for i in range(6) for j in range(6) if i != j]
+    _paf_parity(oracle, gpu_ctx, ids2, seqs2, pairs2, dict(match=-1, mismatch=5, gap_open=8, gap_extend=2, gap2_open=24, gap2_extend=1))
+    gpu_ctx.load_sequences(ids, seqs)
+    with pytest.raises(aw.AllwaveError) as ei:
+        gpu_ctx.align_pairs(aw.make_params(match=1, mismatch=4, gap_open=6, gap_extend=2, gap2_open=None, gap2_extend=None), pairs[:4])
+    assert ei.value.status == aw.AW_EUNSUPPORTED

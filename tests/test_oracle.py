@@ -233,3 +233,38 @@ def test_fast_mode_agrees(oracle):
         a = O.run_pairs(ids, seqs, pairs, p, use_mash=True, threads=4)
         b = O.run_pairs(ids, seqs, pairs, p, use_mash=True, threads=4, fast=True)
         assert a["paf"] == b["paf"] and a["scores"] == b["scores"] and a["work"]["cells"] == b["work"]["cells"]
+
+
+def test_match_score_bonus(oracle):
+    """match_score < 0 (WFA2 penalty shifting, include/aw_wfa2_compat.h): the alignment is optimal for the shifted penalties
+    (independent Gotoh DP) and the reported score is the CIGAR's score under the user's own penalties, matches included"""
+    O = oracle
+    rnd = random.Random(41)
+    for (m, x, o, e, o2, e2) in [(-1, 4, 6, 2, None, None), (-2, 5, 8, 2, 24, 1), (-3, 2, 1, 1, None, None), (-1, 1, 1, 1, None, None)]:
+        p = O.params(m, x, o, e, o2, e2)
+        shifted = O.params(0, 2 * x - 2 * m, 2 * o, 2 * e - m, None if o2 is None else 2 * o2, None if e2 is None else 2 * e2 - m)
+        for _ in range(25):
+            n = rnd.randint(1, 300)
+            a = bytes(rnd.choice(b"ACGT") for _ in range(n))
+            b = bytearray(a)
+            for _ in range(rnd.randint(0, 12)):
+                pos = rnd.randrange(len(b) + 1)
+                k = rnd.random()
+                if k < 0.5 and pos < len(b):
+                    b[pos] = rnd.choice(b"ACGT")
+                elif k < 0.75:
+                    b[pos:pos] = bytes(rnd.choice(b"ACGT") for _ in range(rnd.randint(1, 30)))
+                else:
+                    del b[pos:pos + rnd.randint(1, 30)]
+            b = bytes(b)
+            st, sc, ops, _ = O.wfa_align(p, a, b)
+            assert st == 0
+            n_m, n_x = ops.count(b"M"), ops.count(b"X")
+            assert n_m + n_x + ops.count(b"D") == len(a) and n_m + n_x + ops.count(b"I") == len(b)
+            assert sc == -O.cigar_penalty(p, ops)                      # user's penalties, match bonus included
+            s_shift = O.cigar_penalty(shifted, ops)                    # the penalty the wavefronts minimised
+            assert s_shift == O.gotoh_penalty(shifted, a, b)           # ... optimally
+            assert 2 * sc == -(s_shift + m * (len(a) + len(b)))       # WFA2's score conversion
+    with pytest.raises(Exception):
+        st, sc, ops, _ = O.wfa_align(O.params(1, 4, 6, 2, None, None), b"ACGT", b"ACGT")
+        assert st == 0
