@@ -109,10 +109,17 @@ int main(int argc, char** argv) {
         std::fprintf(stderr, "error: -i/--input is required\n");
         return 2;
     }
+    // ALLWAVE_TIMING=1: wall time of every start-up phase on stderr (where a short job's time goes)
+    const bool timing = std::getenv("ALLWAVE_TIMING") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (timing) std::fprintf(stderr, "[timing] %8.3f s  %s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(), what);
+    };
     try {
         using namespace allwave;
         const SparsificationStrategy sp = parse_sparsification(spars);
         std::vector<Sequence> seqs = read_fasta(input);
+        mark("FASTA read");
         if (!keep_prefixes.empty()) {
             const size_t before = seqs.size(), removed = filter_by_prefixes(seqs, keep_prefixes, true);
             if (removed) std::fprintf(stderr, "Kept sequences with prefixes: %zu -> %zu (prefixes: %s)\n", before, seqs.size(), keep_prefixes.c_str());
@@ -124,7 +131,9 @@ int main(int argc, char** argv) {
             if (seqs.empty()) throw std::invalid_argument("All sequences were excluded by the specified prefixes");
         }
         Context ctx(device);
+        mark("device context created");
         ctx.load(seqs);
+        mark("sequences packed and sketched on the device");
         if (mash_matrix) {  // src/main.rs:280-293: print the mash distance matrix and exit
             print_mash_matrix(ctx, seqs, sp.kind == SparsificationStrategy::TreeSampling ? sp.kmer_size.value_or(15) : 15, stdout);
             return 0;
@@ -155,6 +164,7 @@ int main(int argc, char** argv) {
             for (auto& m : more) others.push_back(m.get());
         }
         AllPairIterator it(ctx, seqs, params, true, !wfa_orientation, sp);
+        mark("pair list built");
         FILE* out = output.empty() ? stdout : std::fopen(output.c_str(), "w");
         if (!out) throw std::runtime_error("cannot open " + output);
         const auto t0 = std::chrono::steady_clock::now();
@@ -168,8 +178,10 @@ int main(int argc, char** argv) {
                 done += n_lines;
             },
             others);
+        mark("last PAF block delivered");
         writer.close();
         if (out != stdout) std::fclose(out);
+        mark("output closed");
         const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (progress) std::fprintf(stderr, "[%.1fs] %zu/%zu (100.0%%) %.1f alignments/sec - Complete!\n", dt, done, it.pair_count(), done / std::max(dt, 1e-9));
     } catch (const std::exception& e) {

@@ -190,7 +190,7 @@ def run_reference(args, rank, world):
         else:
             full = O.pair_list(ids, seqs, kind=kinds["tree"], fraction=float(parts[3]), k_nearest=int(parts[1]), k_farthest=int(parts[2]))
     per_core = cfg["cpu_pairs_per_core"] or 1
-    per_step = max(2, max(1, per_core // 4) * cores) if args.config != "C4" else 2
+    per_step = max(2, per_core * cores) if args.config != "C4" else 2
     pairs = job_pairs(len(seqs), per_step, full)
     p = O.params(*cfg["scores"])
     for _ in range(min(args.warmup, 1)):
@@ -344,6 +344,9 @@ def main():
     blk = aw._cabi.PAF_BLOCK_CB(_blk)
     arr = aw._cabi.make_pairs(pairs)
     chunk = 65536
+    if max(len(x) for x in seqs) <= 1024:  # reads: the product path's rule (allwave_b200/host/allwave.hpp, drive()): 65,536 .. 262,144 pairs per chunk
+        n_chunks = max(1, -(-len(pairs) // 262144), min(12, len(pairs) // 65536))
+        chunk = -(-len(pairs) // n_chunks)
     cursor = {"pos": 0}
 
     def _next(_u, out):
