@@ -418,7 +418,9 @@ def main():
             ak = summ.get("align_kernel", {})
             if summ.get("kernel_source_hash") == kernel_source_hash() and summ.get("config", "C2") == args.config and ak.get("pairs_per_launch"):
                 traffic = ak["dram_bytes_per_launch"] / ak["pairs_per_launch"] * len(pairs)
-                traffic_note = f"ncu --set full capture {summ.get('tag')} ({ak['pairs_per_launch']} pairs per launch), scaled per pair"
+                traffic_note = (f"ncu --set full capture {summ.get('tag')} ({ak['pairs_per_launch']} pairs per launch), scaled per pair; in that capture: "
+                                f"dram throughput {ak.get('dram_throughput_pct', 0):.1f} % of peak, issue slots active {ak.get('issue_active_pct', 0):.1f} %, "
+                                f"{ak.get('inst_executed', 0) / ak['pairs_per_launch'] / 1e6:.0f} M warp instructions per pair")
         except Exception:
             pass
         line = {
