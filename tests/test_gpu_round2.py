@@ -424,3 +424,34 @@ def test_match_score_bonus(oracle, gpu_ctx):
     with pytest.raises(aw.AllwaveError) as ei:
         gpu_ctx.align_pairs(aw.make_params(match=1, mismatch=4, gap_open=6, gap_extend=2, gap2_open=None, gap2_extend=None), pairs[:4])
     assert ei.value.status == aw.AW_EUNSUPPORTED
+
+
+def test_real_wfa2_vectors_gpu(gpu_ctx):
+    """the CUDA path against the output of a real WFA2-lib build (tests/golden/wfa2_lib_vectors.tsv.gz, produced by
+    tools/wfa2_vectors/dump_wfa2_vectors.c); skipped, saying so, until a maintainer with WFA2-lib commits that file"""
+    import gzip
+    here = os.path.dirname(os.path.abspath(__file__))
+    vec = os.environ.get("AW_WFA2_VECTORS") or os.path.join(here, "golden", "wfa2_lib_vectors.tsv.gz")
+    if not os.path.exists(vec):
+        pytest.skip("PARITY UNPINNED: no WFA2-lib vectors in tests/golden/ (see tools/wfa2_vectors/dump_wfa2_vectors.c)")
+    inputs = {}
+    with gzip.open(os.path.join(here, "golden", "wfa2_inputs.tsv.gz"), "rt") as f:
+        for line in f:
+            v = line.rstrip("\n").split("\t")
+            inputs[v[0]] = (tuple(int(x) for x in v[1:7]), v[7].encode(), v[8].encode())
+    by_pen = {}
+    with gzip.open(vec, "rt") as f:
+        for line in f:
+            k, score, ops = (line.rstrip("\n").split("\t") + [""])[:3]
+            by_pen.setdefault(inputs[k][0], []).append((k, int(score), ops))
+    for (m, x, o1, e1, o2, e2), items in by_pen.items():
+        seqs, ids = [], []
+        for k, _, _ in items:
+            seqs += [inputs[k][1], inputs[k][2]]
+            ids += [k + "q", k + "t"]
+        gpu_ctx.load_sequences(ids, seqs)
+        pen = dict(match=m, mismatch=x, gap_open=o1, gap_extend=e1, gap2_open=o2 if o2 >= 0 else None, gap2_extend=e2 if o2 >= 0 else None)
+        res = gpu_ctx.align_pairs(aw.make_params(**pen), [(2 * i, 2 * i + 1) for i in range(len(items))], orientation=aw.AW_ORIENT_FORWARD,
+                                  flags=aw.AW_FLAG_CIGAR_BYTES)
+        for r, (k, score, ops) in zip(res, items):
+            assert r["status"] == 0 and r["score"] == score and r["cigar_bytes"].decode() == ops, k
