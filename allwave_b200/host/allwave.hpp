@@ -10,6 +10,7 @@
 //   extract_tree_pairs, build_knn_graph, generate_random_pairs                          src/knn_graph.rs:12-174
 //   mash distance from Jaccard                                                          src/mash.rs:59-74
 //   the -p grammar of the CLI                                                           src/main.rs:136-203
+//   wfa::{align_sequences, validate_cigar_alignment, Penalties, Mode, Result}           src/wfa.rs:7-258
 // Everything numeric on the alignment path (sketches, Jaccard counts, orientation, wavefronts,
 // CIGAR, PAF text) is computed on the GPU through the C ABI; this header only builds pair lists,
 // partitions them and forwards results.
@@ -668,6 +669,112 @@ inline void process_alignments_with_callback(Context& ctx, const std::vector<Seq
 
 // src/lib.rs:71-112: the PAF line is produced on the GPU together with the CIGAR
 inline const std::string& alignment_to_paf(const AlignmentResult& r, const std::vector<Sequence>&) { return r.paf; }
+
+// ---- src/wfa.rs: the legacy one-pair entry point (test-only caller in the reference), over the aw_aligner_* calls ----
+namespace wfa {
+enum class Mode { EditDistance, SinglePieceAffine, TwoPieceAffine };  // src/wfa.rs:7-12
+struct Penalties {                                                      // src/wfa.rs:27-33
+    int32_t mismatch, gap_opening1, gap_extension1, gap_opening2, gap_extension2;
+};
+struct Result {  // src/wfa.rs:35-47; insertions / deletions in the standard (PAF) convention, i.e. WFA2's D / I
+    int32_t score = 0;
+    std::string cigar;
+    size_t matches = 0, mismatches = 0, insertions = 0, deletions = 0, alignment_length = 0;
+};
+struct AlignmentError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// src/wfa.rs:105-176: the op string must be made of M = X I D only, stay inside both sequences and consume both completely
+// (WFA2 letters: I consumes the reference/text, D the query/pattern).  Returns the reference's message, empty when valid.
+inline std::string validate_cigar_alignment(const uint8_t* cigar, size_t n, size_t query_len, size_t reference_len) {
+    size_t q = 0, r = 0;
+    char buf[160];
+    for (size_t i = 0; i < n; ++i) {
+        const uint8_t op = cigar[i];
+        if (op == 'M' || op == '=' || op == 'X') {
+            if (q >= query_len || r >= reference_len) {
+                std::snprintf(buf, sizeof(buf), "CIGAR extends beyond sequences at M/=/X op: q_pos=%zu, r_pos=%zu, query_len=%zu, ref_len=%zu", q, r, query_len, reference_len);
+                return buf;
+            }
+            ++q;
+            ++r;
+        } else if (op == 'I') {
+            if (r >= reference_len) {
+                std::snprintf(buf, sizeof(buf), "CIGAR extends beyond reference at I op: r_pos=%zu, ref_len=%zu", r, reference_len);
+                return buf;
+            }
+            ++r;
+        } else if (op == 'D') {
+            if (q >= query_len) {
+                std::snprintf(buf, sizeof(buf), "CIGAR extends beyond query at D op: q_pos=%zu, query_len=%zu", q, query_len);
+                return buf;
+            }
+            ++q;
+        } else {
+            std::snprintf(buf, sizeof(buf), "Invalid CIGAR operation: %c (0x%02x)", (char)op, (unsigned)op);
+            return buf;
+        }
+    }
+    if (q != query_len) {
+        std::snprintf(buf, sizeof(buf), "CIGAR doesn't cover full query: %zu vs %zu", q, query_len);
+        return buf;
+    }
+    if (r != reference_len) {
+        std::snprintf(buf, sizeof(buf), "CIGAR doesn't cover full reference: %zu vs %zu", r, reference_len);
+        return buf;
+    }
+    return std::string();
+}
+
+// src/wfa.rs:49-83: run-length encode, M -> '=', X -> 'X', I -> 'D', D -> 'I', anything else '?'
+inline std::string cigar_bytes_to_string(const uint8_t* cigar, size_t n) {
+    std::string out;
+    for (size_t i = 0; i < n;) {
+        size_t j = i + 1;
+        while (j < n && cigar[j] == cigar[i]) ++j;
+        const uint8_t op = cigar[i];
+        out += std::to_string(j - i);
+        out += (op == 'M') ? '=' : (op == 'X') ? 'X' : (op == 'I') ? 'D' : (op == 'D') ? 'I' : '?';
+        i = j;
+    }
+    return out;
+}
+
+// src/wfa.rs:178-258: a fresh aligner per call, configured for an exact global alignment; the CIGAR is validated before use
+inline Result align_sequences(Context& ctx, const std::vector<uint8_t>& pattern, const std::vector<uint8_t>& text, const Penalties& pen, Mode mode) {
+    aw_aligner* wf = nullptr;
+    int rc;
+    if (mode == Mode::EditDistance) rc = aw_aligner_new_affine(ctx.get(), 0, pen.mismatch, pen.mismatch, pen.mismatch, AW_MEMORY_ULTRALOW, &wf);
+    else if (mode == Mode::SinglePieceAffine) rc = aw_aligner_new_affine(ctx.get(), 0, pen.mismatch, pen.gap_opening1, pen.gap_extension1, AW_MEMORY_ULTRALOW, &wf);
+    else rc = aw_aligner_new_affine2p(ctx.get(), 0, pen.mismatch, pen.gap_opening1, pen.gap_extension1, pen.gap_opening2, pen.gap_extension2, AW_MEMORY_ULTRALOW, &wf);
+    if (rc != AW_OK) throw AlignmentError(std::string("Alignment failed with status: ") + aw_strerror(rc) + ": " + aw_last_error());
+    struct Guard {
+        aw_aligner* a;
+        ~Guard() { aw_aligner_delete(a); }
+    } guard{wf};
+    aw_aligner_set_alignment_scope(wf, AW_SCOPE_ALIGNMENT);
+    aw_aligner_set_alignment_span(wf, AW_SPAN_END2END);
+    aw_aligner_set_heuristic(wf, AW_HEURISTIC_NONE);
+    rc = aw_aligner_align(wf, pattern.data(), (int32_t)pattern.size(), text.data(), (int32_t)text.size());
+    if (rc != AW_OK) throw AlignmentError(std::string("Alignment failed with status: ") + aw_strerror(rc));
+    uint64_t n = 0;
+    const uint8_t* ops = aw_aligner_cigar(wf, &n);
+    const std::string bad = validate_cigar_alignment(ops, (size_t)n, pattern.size(), text.size());
+    if (!bad.empty()) throw AlignmentError("CIGAR validation failed: " + bad);
+    Result r;
+    r.score = aw_aligner_score(wf);
+    r.cigar = cigar_bytes_to_string(ops, (size_t)n);
+    for (uint64_t i = 0; i < n; ++i) {  // src/wfa.rs:85-103
+        r.matches += ops[i] == 'M';
+        r.mismatches += ops[i] == 'X';
+        r.deletions += ops[i] == 'I';
+        r.insertions += ops[i] == 'D';
+    }
+    r.alignment_length = r.matches + r.mismatches;
+    return r;
+}
+}  // namespace wfa
 
 // src/alignment.rs:178-190 (API surface only; the aligner uses the device copy)
 inline std::vector<uint8_t> reverse_complement(const std::vector<uint8_t>& seq) {

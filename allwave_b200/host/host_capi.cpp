@@ -251,5 +251,36 @@ int64_t awh_test_cancel(aw_ctx* ctx, uint64_t n, const char* const* ids, const u
     return -1;
 }
 
+// wfa::validate_cigar_alignment (src/wfa.rs:105-176): 0 = valid, else 1 with the reference's message in msg_out
+int awh_validate_cigar(const uint8_t* cigar, uint64_t n, uint64_t query_len, uint64_t reference_len, char* msg_out /*>=160*/) {
+    const std::string m = wfa::validate_cigar_alignment(cigar, (size_t)n, (size_t)query_len, (size_t)reference_len);
+    if (msg_out) std::snprintf(msg_out, 160, "%s", m.c_str());
+    return m.empty() ? 0 : 1;
+}
+
+// wfa::align_sequences (src/wfa.rs:178-258) through the C++ mirror: mode 0 edit, 1 affine, 2 two-piece affine.
+// counts = {matches, mismatches, insertions, deletions, alignment_length}; the cigar string is malloc'ed (awh_free)
+int awh_align_sequences(aw_ctx* ctx, const uint8_t* pattern, uint64_t plen, const uint8_t* text, uint64_t tlen, const int32_t pen[5], int mode, int32_t* score,
+                        uint64_t counts[5], char** cigar_out) {
+    try {
+        Context c(ctx, false);
+        const wfa::Penalties p{pen[0], pen[1], pen[2], pen[3], pen[4]};
+        const wfa::Result r = wfa::align_sequences(c, std::vector<uint8_t>(pattern, pattern + plen), std::vector<uint8_t>(text, text + tlen), p,
+                                                   mode == 0 ? wfa::Mode::EditDistance : mode == 1 ? wfa::Mode::SinglePieceAffine : wfa::Mode::TwoPieceAffine);
+        *score = r.score;
+        counts[0] = r.matches;
+        counts[1] = r.mismatches;
+        counts[2] = r.insertions;
+        counts[3] = r.deletions;
+        counts[4] = r.alignment_length;
+        *cigar_out = (char*)std::malloc(r.cigar.size() + 1);
+        std::memcpy(*cigar_out, r.cigar.c_str(), r.cigar.size() + 1);
+        return 0;
+    } catch (const std::exception& e) {
+        g_msg = e.what();
+        return 1;
+    }
+}
+
 void awh_free(void* p) { std::free(p); }
 }

@@ -40,6 +40,9 @@ def lib():
                                   C.c_int, C.c_uint64, C.c_char_p, C.c_int, C.POINTER(C.c_double)]
         L.awh_test_cancel.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.c_char_p]
         L.awh_test_cancel.restype = C.c_int64
+        L.awh_validate_cigar.argtypes = [C.c_char_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_char_p]
+        L.awh_align_sequences.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32),
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_void_p)]
         L.awh_partition_pairs.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32)]
         _lib = L
     return _lib
@@ -145,3 +148,28 @@ def cancel_probe(ctx, ids, lens, fail_at, chunk_pairs=0):
     msg = C.create_string_buffer(128)
     seen = lib().awh_test_cancel(ctx._h, n, ia, la, fail_at, chunk_pairs, msg)
     return seen, msg.value.decode()
+
+
+def validate_cigar_alignment(cigar: bytes, query_len: int, reference_len: int):
+    """wfa::validate_cigar_alignment (src/wfa.rs:105-176): None when valid, else the reference's message"""
+    msg = C.create_string_buffer(160)
+    rc = lib().awh_validate_cigar(cigar, len(cigar), query_len, reference_len, msg)
+    return None if rc == 0 else msg.value.decode()
+
+
+MODE_EDIT, MODE_AFFINE, MODE_AFFINE2P = 0, 1, 2
+
+
+def align_sequences(ctx, pattern: bytes, text: bytes, mismatch, gap_opening1=0, gap_extension1=0, gap_opening2=0, gap_extension2=0, mode=MODE_AFFINE2P):
+    """wfa::align_sequences (src/wfa.rs:178-258) through the C++ mirror -> dict(score, cigar, matches, mismatches, insertions, deletions,
+    alignment_length); raises RuntimeError with the mirror's message on failure"""
+    pen = (C.c_int32 * 5)(mismatch, gap_opening1, gap_extension1, gap_opening2, gap_extension2)
+    score = C.c_int32()
+    counts = (C.c_uint64 * 5)()
+    cig = C.c_void_p()
+    if lib().awh_align_sequences(ctx._h, pattern, len(pattern), text, len(text), pen, mode, C.byref(score), counts, C.byref(cig)) != 0:
+        raise RuntimeError(lib().awh_last_message().decode())
+    s = C.string_at(cig).decode()
+    lib().awh_free(cig)
+    return dict(score=score.value, cigar=s, matches=int(counts[0]), mismatches=int(counts[1]), insertions=int(counts[2]), deletions=int(counts[3]),
+                alignment_length=int(counts[4]))

@@ -273,3 +273,19 @@ def test_rust_sys_crate_matches_header():
     for cname, val in re.findall(r"\b(AW_[A-Z0-9_]+)\s*=\s*(-?\d+)", hdr) + re.findall(r"#define (AW_FLAG_[A-Z_]+) (\d+)u", hdr):
         m = re.search(r"pub const %s: \w+ = (-?\d+);" % cname, rs)
         assert m and int(m.group(1)) == int(val), cname
+
+
+def test_validate_cigar_alignment_host():
+    """wfa::validate_cigar_alignment of the C++ mirror: the cases and messages of src/wfa.rs:105-176 (WFA2 letters: I consumes
+    the reference, D the query; '=' is accepted beside M and X)"""
+    from allwave_b200 import hostlib as H
+
+    assert H.validate_cigar_alignment(b"MMMXMM", 6, 6) is None
+    assert H.validate_cigar_alignment(b"MM=XIIDM", 6, 7) is None          # query: MM=X + D + M = 6, reference: MM=X + II + M = 7
+    assert H.validate_cigar_alignment(b"", 0, 0) is None
+    assert H.validate_cigar_alignment(b"MMM", 2, 3) == "CIGAR extends beyond sequences at M/=/X op: q_pos=2, r_pos=2, query_len=2, ref_len=3"
+    assert H.validate_cigar_alignment(b"MI", 1, 1) == "CIGAR extends beyond reference at I op: r_pos=1, ref_len=1"
+    assert H.validate_cigar_alignment(b"MD", 1, 1) == "CIGAR extends beyond query at D op: q_pos=1, query_len=1"
+    assert H.validate_cigar_alignment(b"MSM", 3, 3) == "Invalid CIGAR operation: S (0x53)"
+    assert H.validate_cigar_alignment(b"MM", 3, 2) == "CIGAR doesn't cover full query: 2 vs 3"
+    assert H.validate_cigar_alignment(b"MM", 2, 3) == "CIGAR doesn't cover full reference: 2 vs 3"

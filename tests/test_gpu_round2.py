@@ -455,3 +455,28 @@ def test_real_wfa2_vectors_gpu(gpu_ctx):
                                   flags=aw.AW_FLAG_CIGAR_BYTES)
         for r, (k, score, ops) in zip(res, items):
             assert r["status"] == 0 and r["score"] == score and r["cigar_bytes"].decode() == ops, k
+
+
+def test_legacy_align_sequences(oracle, gpu_ctx):
+    """wfa::align_sequences of the C++ mirror (src/wfa.rs:178-258): a fresh aligner per call in each of the three modes; score,
+    standard-convention CIGAR and the five counters against the oracle; the README example of WFA2-lib"""
+    from allwave_b200 import hostlib as H
+
+    r = H.align_sequences(gpu_ctx, b"TCTTTACTCGCGCGTTGGAGAAATACAATAGT", b"TCTATACTGCGCGTTTGGAGAAATAAAATAGT", 4, 6, 2, mode=H.MODE_AFFINE)
+    assert (r["score"], r["cigar"]) == (-24, "3=1X4=1I7=1D9=1X6=")
+    rnd = random.Random(5)
+    for mode, pen in ((H.MODE_EDIT, (3, 0, 0, 0, 0)), (H.MODE_AFFINE, (4, 6, 2, 0, 0)), (H.MODE_AFFINE2P, (5, 8, 2, 24, 1))):
+        for _ in range(6):
+            a = bytes(rnd.choice(b"ACGT") for _ in range(rnd.randint(1, 700)))
+            b = _mutate(rnd, a, 0.08) or b"A"
+            r = H.align_sequences(gpu_ctx, a, b, *pen, mode=mode)
+            if mode == H.MODE_EDIT:
+                p = oracle.params(0, pen[0], pen[0], pen[0], None, None)
+            elif mode == H.MODE_AFFINE:
+                p = oracle.params(0, pen[0], pen[1], pen[2], None, None)
+            else:
+                p = oracle.params(0, *pen)
+            st, sc, ops, _ = oracle.wfa_align(p, a, b)
+            assert st == 0 and r["score"] == sc and r["cigar"] == oracle.cigar_string(ops)
+            assert (r["matches"], r["mismatches"], r["insertions"], r["deletions"]) == (ops.count(b"M"), ops.count(b"X"), ops.count(b"D"), ops.count(b"I"))
+            assert r["alignment_length"] == r["matches"] + r["mismatches"]
