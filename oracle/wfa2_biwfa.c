@@ -253,6 +253,45 @@ static void wf_trim(const aligner_t* a, wf_t* w) {
     }
 }
 
+
+/* fast mode, interior of a wavefront (every read inside the NULL-padded allocations): the elementwise recurrences of
+ * wavefront_compute_affine(2p)_idm over disjoint rows -- restrict-qualified so that the compiler vectorises them, cloned for AVX2
+ * (resolved at load time; the baseline x86-64 clone has no packed 32-bit max) as a WFA2-lib build compiled for the host would be */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define AW_FAST_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define AW_FAST_CLONES
+#endif
+AW_FAST_CLONES
+static void fast_interior_2p(int f_lo, int f_hi, const int32_t* restrict pmx, const int32_t* restrict pmo1, const int32_t* restrict pi1,
+                             const int32_t* restrict pd1, const int32_t* restrict pmo2, const int32_t* restrict pi2, const int32_t* restrict pd2,
+                             int32_t* restrict om, int32_t* restrict oi1, int32_t* restrict od1, int32_t* restrict oi2, int32_t* restrict od2, uint32_t tlen,
+                             uint32_t plen) {
+    for (int q = f_lo; q <= f_hi; ++q) {
+        const int32_t ins1 = MAXI(pmo1[q - 1], pi1[q - 1]) + 1, del1 = MAXI(pmo1[q + 1], pd1[q + 1]);
+        const int32_t ins2 = MAXI(pmo2[q - 1], pi2[q - 1]) + 1, del2 = MAXI(pmo2[q + 1], pd2[q + 1]);
+        oi1[q] = ins1;
+        od1[q] = del1;
+        oi2[q] = ins2;
+        od2[q] = del2;
+        int32_t mx = MAXI(MAXI(del1, del2), MAXI(pmx[q] + 1, MAXI(ins1, ins2)));
+        if ((uint32_t)mx > tlen || (uint32_t)(mx - q) > plen) mx = OFFSET_NULL;
+        om[q] = mx;
+    }
+}
+AW_FAST_CLONES
+static void fast_interior_1p(int f_lo, int f_hi, const int32_t* restrict pmx, const int32_t* restrict pmo1, const int32_t* restrict pi1,
+                             const int32_t* restrict pd1, int32_t* restrict om, int32_t* restrict oi1, int32_t* restrict od1, uint32_t tlen, uint32_t plen) {
+    for (int q = f_lo; q <= f_hi; ++q) {
+        const int32_t ins1 = MAXI(pmo1[q - 1], pi1[q - 1]) + 1, del1 = MAXI(pmo1[q + 1], pd1[q + 1]);
+        oi1[q] = ins1;
+        od1[q] = del1;
+        int32_t mx = MAXI(del1, MAXI(pmx[q] + 1, ins1));
+        if ((uint32_t)mx > tlen || (uint32_t)(mx - q) > plen) mx = OFFSET_NULL;
+        om[q] = mx;
+    }
+}
+
 /* wavefront_compute_affine / wavefront_compute_affine2p (+ _idm kernels, limits_input,
  * allocate_output, process_ends) for one score */
 static void wf_compute(aligner_t* a, int s) {
@@ -318,31 +357,10 @@ static void wf_compute(aligner_t* a, int s) {
             const int32_t* pmo1 = m_o1->off - m_o1->alo;
             const int32_t* pi1 = i1_e->off - i1_e->alo;
             const int32_t* pd1 = d1_e->off - d1_e->alo;
-            if (two) {
-                const int32_t* pmo2 = m_o2->off - m_o2->alo;
-                const int32_t* pi2 = i2_e->off - i2_e->alo;
-                const int32_t* pd2 = d2_e->off - d2_e->alo;
-                for (int q = f_lo; q <= f_hi; ++q) {
-                    const int32_t ins1 = MAXI(pmo1[q - 1], pi1[q - 1]) + 1, del1 = MAXI(pmo1[q + 1], pd1[q + 1]);
-                    const int32_t ins2 = MAXI(pmo2[q - 1], pi2[q - 1]) + 1, del2 = MAXI(pmo2[q + 1], pd2[q + 1]);
-                    oi1[q] = ins1;
-                    od1[q] = del1;
-                    oi2[q] = ins2;
-                    od2[q] = del2;
-                    int32_t mx = MAXI(MAXI(del1, del2), MAXI(pmx[q] + 1, MAXI(ins1, ins2)));
-                    if ((uint32_t)mx > tlen || (uint32_t)(mx - q) > plen) mx = OFFSET_NULL;
-                    om[q] = mx;
-                }
-            } else {
-                for (int q = f_lo; q <= f_hi; ++q) {
-                    const int32_t ins1 = MAXI(pmo1[q - 1], pi1[q - 1]) + 1, del1 = MAXI(pmo1[q + 1], pd1[q + 1]);
-                    oi1[q] = ins1;
-                    od1[q] = del1;
-                    int32_t mx = MAXI(del1, MAXI(pmx[q] + 1, ins1));
-                    if ((uint32_t)mx > tlen || (uint32_t)(mx - q) > plen) mx = OFFSET_NULL;
-                    om[q] = mx;
-                }
-            }
+            if (two)
+                fast_interior_2p(f_lo, f_hi, pmx, pmo1, pi1, pd1, m_o2->off - m_o2->alo, i2_e->off - i2_e->alo, d2_e->off - d2_e->alo, om, oi1, od1, oi2, od2, tlen, plen);
+            else
+                fast_interior_1p(f_lo, f_hi, pmx, pmo1, pi1, pd1, om, oi1, od1, tlen, plen);
             k = f_hi;
             continue;
         }
