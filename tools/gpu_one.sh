@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests -m gpu -q -k "legacy_align or aligner_api or match_score" > gpurun_out/one_tests.log 2>&1; echo "exit $?" >> gpurun_out/one_tests.log; tail -15 gpurun_out/one_tests.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/one_smoke.log 2>&1; tail -2 gpurun_out/one_smoke.log
+timeout 120 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/one_reference.json 2> gpurun_out/one_reference.err; cut -c1-200 gpurun_out/one_reference.json; tail -2 gpurun_out/one_reference.err
