@@ -17,7 +17,7 @@ biWFA -> CIGAR -> PAF text) over one batch of `--batch` pairs per GPU drawn from
             bandwidth, with SURVEY 8(d)'s algorithmic bytes per pair.
   cpu_baseline / --impl reference
             the CPU restatement of the allwave/WFA2 path (oracle/, "port": the Rust reference cannot be built in this
-            image), all host threads, on a bounded sample of the same pairs.
+            image), all host threads, on a bounded sample of the same pairs (in the N=1 line only).
 """
 import argparse
 import hashlib
@@ -441,7 +441,7 @@ def main():
                          "note": "compulsory HBM traffic of this path is tiny (SURVEY 8d): the kernel is bound by memory latency + integer issue, see profiles/"},
         }
         sample = cpu_sample_pairs(args.config, pairs, os.cpu_count() or 1)
-        if not args.no_cpu_baseline and sample:
+        if not args.no_cpu_baseline and sample and world == 1:  # the CPU leg belongs to the N=1 line only (idle ranks would share its cores)
             import oracle_lib as O
 
             cores = os.cpu_count() or 1
