@@ -14,6 +14,8 @@ timeout 900 python bench.py --config C4 --steps 1 --warmup 1 --no-cpu-baseline >
 B="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $B > gpurun_out/final_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/final_launches.csv $B > gpurun_out/final_ncu_launches.log 2>&1
+# NOTE: the full-set capture replays the 4 s kernel ~40 times with a save/restore of its multi-GB workspace: it took 32 minutes of box
+# time in round 2 (everything above it: 10 minutes).  `--batch 2368` would cut that sixfold at the cost of a longer tail in the profile.
 B1="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --e2e-steps 1"
 $B1 > gpurun_out/final_plain1.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:aw_align_kernel -s 3 -c 1 -o gpurun_out/prof_final_align $B1 > gpurun_out/final_ncu_full.log 2>&1
